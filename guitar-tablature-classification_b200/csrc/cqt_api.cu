@@ -1,0 +1,217 @@
+// C-ABI entry points of the segment CQT (plan, workspace, frame -> GEMM -> finish) and library-wide helpers.
+#include <stdarg.h>
+#include <math.h>
+#include <new>
+#include <vector>
+#include "gtc_common.cuh"
+
+namespace gtc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count_of_current_device() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    set_error("no usable CUDA device (libgtc has no CPU fallback): %s", cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  return sms;
+}
+
+static inline float tf32_rn_host(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x00000fffu + ((u >> 13) & 1u)) & 0xffffe000u;
+  float y;
+  memcpy(&y, &u, 4);
+  return y;
+}
+
+struct Workspace {
+  int64_t n_rows, n_rows_pad, n_rows_alloc;
+  size_t off_xhi, off_xlo, off_out, off_rowmax, total;
+};
+
+static Workspace workspace_layout(const PlanImpl& p, int64_t n_seg, int64_t n_clips, bool complex_out) {
+  Workspace w;
+  w.n_rows = n_seg + n_clips * (p.parts - 1);
+  w.n_rows_pad = round_up(w.n_rows > 0 ? w.n_rows : 1, 128);
+  w.n_rows_alloc = w.n_rows_pad + 8;                    // rows read with the +p offset of the last tile
+  const size_t xbytes = (size_t)w.n_rows_alloc * p.kp * sizeof(float);
+  const size_t obytes = (size_t)w.n_rows_pad * (complex_out ? p.n_out : p.n_out / 2) * sizeof(float);
+  size_t o = 0;
+  auto take = [&](size_t b) { size_t at = o; o += (b + 1023) & ~(size_t)1023; return at; };
+  w.off_xhi = take(xbytes);
+  w.off_xlo = take(xbytes);
+  w.off_out = take(obytes);
+  w.off_rowmax = take((size_t)w.n_rows_pad * sizeof(float));
+  w.total = o;
+  return w;
+}
+
+}  // namespace gtc
+
+using namespace gtc;
+
+struct gtc_plan {
+  PlanImpl impl;
+};
+
+extern "C" int gtc_version(void) { return GTC_VERSION; }
+extern "C" const char* gtc_last_error(void) { return g_err; }
+
+extern "C" int gtc_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
+  cudaDeviceProp prop;
+  GTC_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (total_mem) *total_mem = prop.totalGlobalMem;
+  return GTC_OK;
+}
+
+extern "C" int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int seg_hop, int n_bins, int n_frames,
+                                   const float* h_operator, int gemm_engine) {
+  GTC_REQUIRE(out != nullptr, GTC_E_ARG, "gtc_cqt_plan_create: out is NULL");
+  *out = nullptr;
+  GTC_REQUIRE(h_operator != nullptr, GTC_E_ARG, "gtc_cqt_plan_create: h_operator is NULL (design it with gtc_b200.cqt_design)");
+  GTC_REQUIRE(seg_len > 0 && seg_hop > 0 && n_bins > 0 && n_frames > 0, GTC_E_ARG, "gtc_cqt_plan_create: non-positive size");
+  GTC_REQUIRE(gemm_engine == GTC_GEMM_TCGEN05_3XTF32 || gemm_engine == GTC_GEMM_SIMT_FP32, GTC_E_ARG,
+              "gtc_cqt_plan_create: unknown engine %d", gemm_engine);
+  GTC_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GTC_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  GTC_REQUIRE(prop.major == 10, GTC_E_UNSUP, "libgtc is built for sm_100a only; device %d is sm_%d%d", device, prop.major,
+              prop.minor);
+
+  gtc_plan* plan = new (std::nothrow) gtc_plan();
+  GTC_REQUIRE(plan != nullptr, GTC_E_NOMEM, "gtc_cqt_plan_create: out of host memory");
+  PlanImpl& p = plan->impl;
+  memset(&p, 0, sizeof(p));
+  p.device = device;
+  p.seg_len = seg_len; p.seg_hop = seg_hop; p.n_bins = n_bins; p.n_frames = n_frames;
+  const bool divides = (seg_len % seg_hop == 0) && (seg_len / seg_hop <= 8);
+  p.parts = divides ? seg_len / seg_hop : 1;
+  p.row_len = divides ? seg_hop : seg_len;
+  p.kp = (int)round_up(p.row_len, 32);
+  p.k_total = p.parts * p.kp;
+  p.n_out = 2 * n_bins * n_frames;
+  p.n_pad = (int)round_up(p.n_out, 128);
+  p.engine = gemm_engine;
+  p.sm_count = prop.multiProcessorCount;
+  if (gemm_engine == GTC_GEMM_TCGEN05_3XTF32 && (p.n_out % 16 != 0)) {
+    delete plan;
+    set_error("gtc_cqt_plan_create: tcgen05 engine needs 2*n_bins*n_frames %% 16 == 0 (got %d)", p.n_out);
+    return GTC_E_UNSUP;
+  }
+
+  const size_t elems = (size_t)p.n_pad * p.k_total;
+  std::vector<float> raw(elems, 0.f), hi(elems, 0.f), lo(elems, 0.f);
+  for (int n = 0; n < p.n_out; ++n) {
+    const float* src = h_operator + (size_t)n * seg_len;
+    float* r = raw.data() + (size_t)n * p.k_total;
+    float* h = hi.data() + (size_t)n * p.k_total;
+    float* l = lo.data() + (size_t)n * p.k_total;
+    for (int j = 0; j < seg_len; ++j) {
+      const int part = j / p.row_len, k = j - part * p.row_len;
+      const size_t at = (size_t)part * p.kp + k;
+      const float v = src[j];
+      r[at] = v;
+      h[at] = tf32_rn_host(v);
+      l[at] = v - h[at];
+    }
+  }
+  int rc = GTC_OK;
+  auto up = [&](float** d, const std::vector<float>& h) -> int {
+    GTC_CUDA_CHECK(cudaMalloc((void**)d, elems * sizeof(float)));
+    GTC_CUDA_CHECK(cudaMemcpy(*d, h.data(), elems * sizeof(float), cudaMemcpyHostToDevice));
+    return GTC_OK;
+  };
+  if ((rc = up(&p.d_op, raw)) != GTC_OK || (rc = up(&p.d_op_hi, hi)) != GTC_OK || (rc = up(&p.d_op_lo, lo)) != GTC_OK) {
+    gtc_cqt_plan_destroy(plan);
+    return rc;
+  }
+  if (gemm_engine == GTC_GEMM_TCGEN05_3XTF32 && (rc = tc_plan_init(p)) != GTC_OK) {
+    gtc_cqt_plan_destroy(plan);
+    return rc;
+  }
+  *out = plan;
+  return GTC_OK;
+}
+
+extern "C" int gtc_cqt_plan_destroy(gtc_plan* plan) {
+  if (!plan) return GTC_OK;
+  PlanImpl& p = plan->impl;
+  tc_plan_free(p);
+  if (p.d_op) cudaFree(p.d_op);
+  if (p.d_op_hi) cudaFree(p.d_op_hi);
+  if (p.d_op_lo) cudaFree(p.d_op_lo);
+  delete plan;
+  return GTC_OK;
+}
+
+extern "C" int gtc_cqt_plan_parts(const gtc_plan* plan) { return plan ? plan->impl.parts : GTC_E_ARG; }
+
+extern "C" int gtc_cqt_workspace_bytes(const gtc_plan* plan, int64_t n_seg, int64_t n_clips, size_t* bytes) {
+  GTC_REQUIRE(plan && bytes && n_seg >= 0 && n_clips >= 0, GTC_E_ARG, "gtc_cqt_workspace_bytes: bad argument");
+  *bytes = workspace_layout(plan->impl, n_seg, n_clips, true).total;     // complex layout is the larger one
+  return GTC_OK;
+}
+
+static int run_segments(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
+                        int64_t n_clips, int64_t n_seg, float* d_out, bool complex_out, void* d_workspace,
+                        size_t workspace_bytes, float power, float amin, float top_db, float cut_db, float floor_db,
+                        cudaStream_t st) {
+  GTC_REQUIRE(plan != nullptr, GTC_E_ARG, "gtc_cqt_segments: plan is NULL");
+  GTC_REQUIRE(n_clips >= 0 && n_seg >= 0, GTC_E_ARG, "gtc_cqt_segments: negative sizes");
+  if (n_seg == 0) return GTC_OK;
+  GTC_REQUIRE(n_clips > 0 && n_clips < (1 << 30), GTC_E_ARG, "gtc_cqt_segments: n_clips out of range");
+  GTC_REQUIRE(d_audio && d_clip_off && d_seg_off && d_out && d_workspace, GTC_E_ARG, "gtc_cqt_segments: null pointer");
+  const PlanImpl& p = plan->impl;
+  const Workspace w = workspace_layout(p, n_seg, n_clips, complex_out);
+  GTC_REQUIRE(workspace_bytes >= w.total, GTC_E_NOMEM, "gtc_cqt_segments: workspace of %zu bytes, %zu needed",
+              workspace_bytes, w.total);
+  GTC_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 1023) == 0, GTC_E_ARG, "gtc_cqt_segments: workspace must be 1024-byte aligned");
+  int dev = -1;
+  GTC_CUDA_CHECK(cudaGetDevice(&dev));
+  GTC_REQUIRE(dev == p.device, GTC_E_ARG, "gtc_cqt_segments: plan belongs to device %d, current device is %d", p.device, dev);
+  char* ws = static_cast<char*>(d_workspace);
+  float* xhi = reinterpret_cast<float*>(ws + w.off_xhi);
+  float* xlo = reinterpret_cast<float*>(ws + w.off_xlo);
+  float* gout = reinterpret_cast<float*>(ws + w.off_out);
+  float* rowmax = reinterpret_cast<float*>(ws + w.off_rowmax);
+  int rc = launch_frame(p, d_audio, d_clip_off, d_seg_off, (int)n_clips, w.n_rows, w.n_rows_alloc, xhi, xlo, rowmax, st);
+  if (rc != GTC_OK) return rc;
+  float* mag2 = complex_out ? nullptr : gout;
+  float* cplx = complex_out ? gout : nullptr;
+  if (p.engine == GTC_GEMM_TCGEN05_3XTF32)
+    rc = launch_gemm_tc(p, xhi, xlo, w.n_rows_pad, w.n_rows_alloc, mag2, cplx, rowmax, st);
+  else
+    rc = launch_gemm_simt(p, xhi, xlo, w.n_rows_pad, mag2, cplx, rowmax, st);
+  if (rc != GTC_OK) return rc;
+  if (complex_out) return launch_finish_complex(p, cplx, d_seg_off, (int)n_clips, n_seg, d_out, st);
+  return launch_finish_db(p, mag2, rowmax, d_seg_off, (int)n_clips, n_seg, d_out, power, amin, top_db, cut_db, floor_db, st);
+}
+
+extern "C" int gtc_cqt_segments_db(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off,
+                                   const int64_t* d_seg_off, int64_t n_clips, int64_t n_seg, float* d_out_db,
+                                   void* d_workspace, size_t workspace_bytes, float power, float amin, float top_db,
+                                   float cut_db, float floor_db, gtc_stream_t stream) {
+  GTC_REQUIRE(power > 0.f && amin > 0.f, GTC_E_ARG, "gtc_cqt_segments_db: power and amin must be positive");
+  return run_segments(plan, d_audio, d_clip_off, d_seg_off, n_clips, n_seg, d_out_db, false, d_workspace, workspace_bytes,
+                      power, amin, top_db, cut_db, floor_db, (cudaStream_t)stream);
+}
+
+extern "C" int gtc_cqt_segments_complex(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off,
+                                        const int64_t* d_seg_off, int64_t n_clips, int64_t n_seg, float* d_out_c,
+                                        void* d_workspace, size_t workspace_bytes, gtc_stream_t stream) {
+  return run_segments(plan, d_audio, d_clip_off, d_seg_off, n_clips, n_seg, d_out_c, true, d_workspace, workspace_bytes,
+                      4.f, 1e-5f, 80.f, -60.f, -120.f, (cudaStream_t)stream);
+}

@@ -1,0 +1,149 @@
+// Framing (audio -> row matrix, tf32 hi/lo split) and the dB epilogue finish of the segment CQT.
+//
+// Framing: a segment of seg_len samples with hop seg_hop = seg_len / P is P consecutive "audio rows" of seg_hop
+// samples, so the GEMM's M operand is the NON-overlapping row matrix and every audio sample is read once
+// (/root/reference/cqt.py:26-45 re-slices each sample into two windows).  Clip c owns rows
+// [seg_off[c] + c*(P-1), seg_off[c+1] + (c+1)*(P-1)); row r of the clip starts at sample clip_off[c] + r*seg_hop.
+// Rows are padded to kp floats (multiple of 32 = one 128-byte TMA/UMMA swizzle atom) and written twice:
+//   hi = x rounded to tf32 (RN, low 13 mantissa bits zero), lo = x - hi (exact in fp32)      -> 3xTF32 operands.
+//
+// Finish: per segment, mag2 = |C|^2 of all n_bins*T outputs plus the row maximum -> |C|^power ->
+// librosa.amplitude_to_db(ref=np.amax, amin, top_db) -> cqt_lim (cqt.py:56-58), written as [n_seg, n_bins, T].
+#include "gtc_common.cuh"
+
+namespace gtc {
+
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u = __float_as_uint(x);
+  u = (u + 0x00000fffu + ((u >> 13) & 1u)) & 0xffffe000u;     // round to nearest even on the 13 dropped bits
+  return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(256)
+frame_kernel(const float* __restrict__ audio, const int64_t* __restrict__ clip_off, const int64_t* __restrict__ seg_off,
+             int n_clips, int parts, int row_len, int seg_hop, int kp, int64_t n_rows, int64_t n_rows_alloc,
+             float* __restrict__ xhi, float* __restrict__ xlo, float* __restrict__ rowmax, int64_t n_rowmax) {
+  const int vec_per_row = kp >> 2;
+  const int64_t total = n_rows_alloc * vec_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / vec_per_row;
+    const int k0 = (int)(i - row * vec_per_row) << 2;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < n_rows) {
+      // clip of this row: rows of clip c start at seg_off[c] + c*(P-1)
+      int lo = 0, hi = n_clips;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(seg_off + mid) + (int64_t)mid * (parts - 1) <= row) lo = mid; else hi = mid;
+      }
+      const int64_t r = row - (__ldg(seg_off + lo) + (int64_t)lo * (parts - 1));
+      const int64_t clip_end = __ldg(clip_off + lo + 1);
+      const int64_t base = __ldg(clip_off + lo) + r * seg_hop + k0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k0 + j < row_len && base + j < clip_end) v[j] = __ldg(audio + base + j);
+    }
+    float4 h, l;
+    h.x = tf32_rn(v[0]); h.y = tf32_rn(v[1]); h.z = tf32_rn(v[2]); h.w = tf32_rn(v[3]);
+    l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
+    reinterpret_cast<float4*>(xhi)[i] = h;
+    reinterpret_cast<float4*>(xlo)[i] = l;
+    if (k0 == 0 && row < n_rowmax) rowmax[row] = 0.f;
+  }
+}
+
+int launch_frame(const PlanImpl& p, const float* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
+                 int n_clips, int64_t n_rows, int64_t n_rows_alloc, float* d_xhi, float* d_xlo, float* d_rowmax,
+                 cudaStream_t st) {
+  const int64_t total = n_rows_alloc * (p.kp / 4);
+  int64_t blocks = ceil_div(total, 256);
+  const int64_t cap = (int64_t)p.sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  const int64_t n_rowmax = round_up(n_rows, 128);
+  frame_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_audio, d_clip_off, d_seg_off, n_clips, p.parts, p.row_len, p.seg_hop,
+                                                  p.kp, n_rows, n_rows_alloc, d_xhi, d_xlo, d_rowmax, n_rowmax);
+  GTC_CUDA_CHECK(cudaGetLastError());
+  return GTC_OK;
+}
+
+// one warp per segment
+__global__ void __launch_bounds__(256)
+finish_db_kernel(const float* __restrict__ mag2, const float* __restrict__ rowmax, const int64_t* __restrict__ seg_off,
+                 int n_clips, int parts, int64_t n_seg, int n_bins, int n_frames, float* __restrict__ out,
+                 float power, float amin, float top_db, float cut_db, float floor_db) {
+  const int lane = threadIdx.x & 31;
+  const int n_mag = n_bins * n_frames;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float amin2 = amin * amin;
+  for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < n_seg; g += warps_total) {
+    const int c = find_clip(seg_off, n_clips, g);
+    const int64_t row = g + (int64_t)c * (parts - 1);
+    const float* src = mag2 + row * n_mag;
+    // S = |C|^power ; amplitude_to_db squares it again: 10*log10(max(amin^2, S^2)) - 10*log10(max(amin^2, ref^2))
+    const float m2max = rowmax[row];
+    auto s_of = [&](float m2) -> float {
+      // |C|^power from |C|^2 : power 4 -> m2*m2 ; power 2 -> m2 ; power 1 -> sqrt(m2) ; else powf
+      if (power == 4.f) return m2 * m2;
+      if (power == 2.f) return m2;
+      if (power == 1.f) return sqrtf(m2);
+      return powf(m2, 0.5f * power);
+    };
+    const float ref = s_of(m2max);
+    const float ref_db = 10.f * log10f(fmaxf(amin2, ref * ref));
+    // log_spec.max() is the peak element's own value, max(amin^2, ref^2) -> exactly 0 dB
+    const float lo_clamp = 0.f - top_db;
+    float* dst = out + g * n_mag;
+    for (int o = lane; o < n_mag; o += 32) {
+      // out is [bin][t]; mag2 is [t][bin]
+      const int bin = o / n_frames, t = o - bin * n_frames;
+      const float s = s_of(src[t * n_bins + bin]);
+      float db = 10.f * log10f(fmaxf(amin2, s * s)) - ref_db;
+      db = fmaxf(db, lo_clamp);
+      if (db < cut_db) db = floor_db;
+      dst[o] = db;
+    }
+  }
+}
+
+int launch_finish_db(const PlanImpl& p, const float* d_mag2, const float* d_rowmax, const int64_t* d_seg_off,
+                     int n_clips, int64_t n_seg, float* d_out_db, float power, float amin, float top_db, float cut_db,
+                     float floor_db, cudaStream_t st) {
+  int64_t blocks = ceil_div(n_seg, 8);
+  const int64_t cap = (int64_t)p.sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  finish_db_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_mag2, d_rowmax, d_seg_off, n_clips, p.parts, n_seg, p.n_bins,
+                                                      p.n_frames, d_out_db, power, amin, top_db, cut_db, floor_db);
+  GTC_CUDA_CHECK(cudaGetLastError());
+  return GTC_OK;
+}
+
+__global__ void __launch_bounds__(256)
+finish_complex_kernel(const float* __restrict__ cplx, const int64_t* __restrict__ seg_off, int n_clips, int parts,
+                      int64_t n_seg, int n_bins, int n_frames, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int n_mag = n_bins * n_frames;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < n_seg; g += warps_total) {
+    const int c = find_clip(seg_off, n_clips, g);
+    const int64_t row = g + (int64_t)c * (parts - 1);
+    const float2* src = reinterpret_cast<const float2*>(cplx + row * 2 * n_mag);
+    float2* dst = reinterpret_cast<float2*>(out + g * 2 * n_mag);
+    for (int o = lane; o < n_mag; o += 32) {
+      const int bin = o / n_frames, t = o - bin * n_frames;
+      dst[o] = src[t * n_bins + bin];
+    }
+  }
+}
+
+int launch_finish_complex(const PlanImpl& p, const float* d_cplx, const int64_t* d_seg_off, int n_clips, int64_t n_seg,
+                          float* d_out, cudaStream_t st) {
+  int64_t blocks = ceil_div(n_seg, 8);
+  const int64_t cap = (int64_t)p.sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  finish_complex_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_cplx, d_seg_off, n_clips, p.parts, n_seg, p.n_bins,
+                                                           p.n_frames, d_out);
+  GTC_CUDA_CHECK(cudaGetLastError());
+  return GTC_OK;
+}
+
+}  // namespace gtc

@@ -1,0 +1,355 @@
+// Tensor-core engine for the segment-operator contraction (GTC_GEMM_TCGEN05_3XTF32), sm_100a only.
+//
+//     C[row][n] = sum_p sum_k X[row + p][k] * Op[n][p*kp + k]          (row = audio row, n = operator row)
+//
+// 3xTF32: X = Xhi + Xlo, Op = Ohi + Olo with *hi exactly representable in tf32, and
+//     C ~= Xhi*Ohi + Xlo*Ohi + Xhi*Olo        (the dropped Xlo*Olo term is ~2^-22 relative)
+// accumulated in fp32 in TMEM.  Per CTA tile: 128 rows x NC operator rows (NC <= 256, one tcgen05.mma N).
+//
+// Warp roles (192 threads, persistent CTAs, one per SM):
+//   warp 0      TMA producer : cp.async.bulk.tensor 2D tiles (128B swizzle) of Xhi/Xlo/Ohi/Olo into a smem ring
+//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=NC, K=8), commits to mbarriers;
+//                              also owns the TMEM allocation (512 columns = 2 accumulator stages)
+//   warps 2..5  epilogue     : tcgen05.ld 32x32b (thread = one row), re^2+im^2, row max, direct global stores
+// The second audio row of a segment (hop = window/2, cqt.py:26-27) is just the TMA row coordinate + p.
+#include <cuda.h>
+#include "gtc_common.cuh"
+
+namespace gtc {
+
+constexpr int TBM = 128;             // rows per tile (UMMA M)
+constexpr int TBK = 32;              // fp32 per k-block = 128 bytes = one swizzle row
+constexpr int TMAXN = 256;           // max operator rows per tile (UMMA N)
+constexpr int TSTAGES = 2;
+constexpr int TUMMA_K = 8;           // tf32
+constexpr uint32_t X_TILE_BYTES = TBM * TBK * 4;        // 16 KB
+constexpr uint32_t OP_TILE_BYTES = TMAXN * TBK * 4;     // 32 KB (NC rows used)
+constexpr uint32_t STAGE_BYTES = 2 * X_TILE_BYTES + 2 * OP_TILE_BYTES;   // 96 KB
+constexpr uint32_t TC_SMEM_BYTES = TSTAGES * STAGE_BYTES + 1024 /*align slack*/;
+constexpr int TC_THREADS = 192;
+
+struct TcParams {
+  int nc;                // operator rows per tile
+  int n_chunks;          // tiles along N
+  int n_out;             // valid operator rows
+  int kb_per_part;       // kp / 32
+  int parts;
+  int64_t m_tiles;
+  float* mag2;           // [rows][n_out/2] or null
+  float* cplx;           // [rows][n_out]   or null
+  float* rowmax;         // [rows]
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);          // start address  [0,14)
+  d |= (uint64_t)1 << 16;                               // leading byte offset (ignored for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset = 8 rows * 128 B              [32,46)
+  d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)                      [46,48)
+  d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B                         [61,64)
+  return d;
+}
+// cute::UMMA::InstrDescriptor : c=F32, a=b=TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <bool kComplex>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
+               const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo,
+               const TcParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_bars[2 * TSTAGES + 4];
+  __shared__ uint32_t s_tmem_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // stage s : [Xhi 16K][Xlo 16K][Ohi 32K][Olo 32K]
+  auto st_xhi = [&](int s) { return smem_base + s * STAGE_BYTES; };
+  auto st_xlo = [&](int s) { return smem_base + s * STAGE_BYTES + X_TILE_BYTES; };
+  auto st_ohi = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * X_TILE_BYTES; };
+  auto st_olo = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * X_TILE_BYTES + OP_TILE_BYTES; };
+  const uint32_t bar_base = smem_u32(s_bars);
+  auto bar_full = [&](int s) { return bar_base + 8 * s; };
+  auto bar_empty = [&](int s) { return bar_base + 8 * (TSTAGES + s); };
+  auto bar_tfull = [&](int a) { return bar_base + 8 * (2 * TSTAGES + a); };
+  auto bar_tempty = [&](int a) { return bar_base + 8 * (2 * TSTAGES + 2 + a); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TSTAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_slot;
+
+  const int nkb = prm.parts * prm.kb_per_part;
+  const int64_t n_tiles = prm.m_tiles * prm.n_chunks;
+  const uint32_t stage_tx = 2 * X_TILE_BYTES + 2 * (uint32_t)prm.nc * TBK * 4;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_xhi)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_xlo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_ohi)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_olo)) : "memory");
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t m_tile = tile / prm.n_chunks;
+        const int chunk = (int)(tile - m_tile * prm.n_chunks);
+        const int row0 = (int)(m_tile * TBM);
+        const int n0 = chunk * prm.nc;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(bar_empty(stage), phase ^ 1);
+          mbar_expect_tx(bar_full(stage), stage_tx);
+          const int p = kb / prm.kb_per_part;
+          const int kx = (kb - p * prm.kb_per_part) * TBK;
+          tma_load_2d(st_xhi(stage), &tm_xhi, bar_full(stage), kx, row0 + p);
+          tma_load_2d(st_xlo(stage), &tm_xlo, bar_full(stage), kx, row0 + p);
+          tma_load_2d(st_ohi(stage), &tm_ohi, bar_full(stage), kb * TBK, n0);
+          tma_load_2d(st_olo(stage), &tm_olo, bar_full(stage), kb * TBK, n0);
+          if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TBM, prm.nc);
+      int stage = 0; uint32_t phase = 0;
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int acc = (int)(it & 1);
+        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(bar_tempty(acc), acc_phase ^ 1);         // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * TMAXN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(bar_full(stage), phase);
+          tc_fence_after();
+          const uint64_t dxh = make_sw128_desc(st_xhi(stage)), dxl = make_sw128_desc(st_xlo(stage));
+          const uint64_t doh = make_sw128_desc(st_ohi(stage)), dol = make_sw128_desc(st_olo(stage));
+#pragma unroll
+          for (int k = 0; k < TBK / TUMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * TUMMA_K * 4) >> 4);     // +32 B per k-step inside the swizzle row
+            umma_tf32(tmem_d, dxh + adv, doh + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_tf32(tmem_d, dxl + adv, doh + adv, idesc, 1u);
+            umma_tf32(tmem_d, dxh + adv, dol + adv, idesc, 1u);
+          }
+          umma_commit(bar_empty(stage));                    // frees the smem slot when these MMAs retire
+          if (kb == nkb - 1) umma_commit(bar_tfull(acc));   // accumulator complete
+          if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+    const int n_mag = prm.n_out >> 1;
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int acc = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      const int64_t m_tile = tile / prm.n_chunks;
+      const int chunk = (int)(tile - m_tile * prm.n_chunks);
+      const int64_t row = m_tile * TBM + q * 32 + lane;
+      const int n0 = chunk * prm.nc;
+      mbar_wait(bar_tfull(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TMAXN;
+      float rmax = 0.f;
+      for (int c = 0; c < prm.nc; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c, r);
+        tmem_ld_wait();
+        const int n = n0 + c;
+        if (n < prm.n_out) {
+          if (kComplex) {
+            float4* dst = reinterpret_cast<float4*>(prm.cplx + row * prm.n_out + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          } else {
+            float m[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float re = __uint_as_float(r[2 * j]), im = __uint_as_float(r[2 * j + 1]);
+              m[j] = re * re + im * im;
+              rmax = fmaxf(rmax, m[j]);
+            }
+            float4* dst = reinterpret_cast<float4*>(prm.mag2 + row * n_mag + (n >> 1));
+            dst[0] = make_float4(m[0], m[1], m[2], m[3]);
+            dst[1] = make_float4(m[4], m[5], m[6], m[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty(acc));
+      if (!kComplex) atomicMax(reinterpret_cast<int*>(prm.rowmax + row), __float_as_int(rmax));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !p) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2D fp32 row-major [rows][cols] tensor, box = 32 floats x box_rows, 128-byte swizzle, OOB -> zeros
+static int encode_2d(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return GTC_E_CUDA;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TBK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GTC_REQUIRE(r == CUDA_SUCCESS, GTC_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return GTC_OK;
+}
+
+static int pick_nc(int n_out) {
+  for (int nc = 256; nc >= 16; nc -= 16)
+    if (n_out % nc == 0) return nc;
+  return 256;
+}
+
+int tc_plan_init(PlanImpl& p) {
+  CUtensorMap* maps = new CUtensorMap[2];
+  p.tmap_op_hi = &maps[0];
+  p.tmap_op_lo = &maps[1];
+  const int nc = pick_nc(p.n_out);
+  int rc = encode_2d(&maps[0], p.d_op_hi, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)nc);
+  if (rc != GTC_OK) return rc;
+  rc = encode_2d(&maps[1], p.d_op_lo, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)nc);
+  if (rc != GTC_OK) return rc;
+  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+  return GTC_OK;
+}
+
+void tc_plan_free(PlanImpl& p) {
+  if (p.tmap_op_hi) delete[] reinterpret_cast<CUtensorMap*>(p.tmap_op_hi);
+  p.tmap_op_hi = p.tmap_op_lo = nullptr;
+}
+
+int launch_gemm_tc(const PlanImpl& p, const float* d_xhi, const float* d_xlo, int64_t n_rows_pad, int64_t n_rows_alloc,
+                   float* d_mag2, float* d_cplx, float* d_rowmax, cudaStream_t st) {
+  GTC_REQUIRE(p.tmap_op_hi != nullptr, GTC_E_ARG, "plan was not created with the tcgen05 engine");
+  CUtensorMap tm_xhi, tm_xlo;
+  int rc = encode_2d(&tm_xhi, d_xhi, (uint64_t)n_rows_alloc, (uint64_t)p.kp, TBM);
+  if (rc != GTC_OK) return rc;
+  rc = encode_2d(&tm_xlo, d_xlo, (uint64_t)n_rows_alloc, (uint64_t)p.kp, TBM);
+  if (rc != GTC_OK) return rc;
+  TcParams prm;
+  prm.nc = pick_nc(p.n_out);
+  prm.n_chunks = (int)ceil_div(p.n_out, prm.nc);
+  prm.n_out = p.n_out;
+  prm.kb_per_part = p.kp / TBK;
+  prm.parts = p.parts;
+  prm.m_tiles = n_rows_pad / TBM;
+  prm.mag2 = d_mag2; prm.cplx = d_cplx; prm.rowmax = d_rowmax;
+  const int64_t n_tiles = prm.m_tiles * prm.n_chunks;
+  const unsigned grid = (unsigned)(n_tiles < p.sm_count ? n_tiles : p.sm_count);
+  const CUtensorMap& tm_ohi = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_hi);
+  const CUtensorMap& tm_olo = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_lo);
+  if (d_cplx)
+    gemm_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
+  else
+    gemm_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
+  GTC_CUDA_CHECK(cudaGetLastError());
+  return GTC_OK;
+}
+
+}  // namespace gtc

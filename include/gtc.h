@@ -1,0 +1,123 @@
+/*
+ * gtc.h -- C ABI of libgtc.so, the B200 (sm_100a) hot path of the guitar-tablature feature front-end.
+ *
+ * The reference (AshishBhardwaj01/Guitar-Tablature-Classification) is pure Python and has no FFI; its
+ * "operator interface" for this path is the Python module API of cqt.py / new_cqt.py / jam_to_tablature.py /
+ * my_dataloader.py / ViT_dataloader.py.  Each entry point below replaces the *library arithmetic* behind one of
+ * those call sites; the Python drop-in modules in guitar-tablature-classification_b200/ bind them with ctypes
+ * (see INTEGRATION.md for the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all `d_*` pointers are DEVICE pointers owned by the caller,
+ *     all `h_*` pointers are HOST pointers.  The library never allocates or frees caller-visible memory;
+ *     scratch memory is passed in as a caller-owned workspace.
+ *   - every function returns 0 on success, <0 on error (GTC_E_*); gtc_last_error() gives a thread-local message.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it.
+ *   - a plan is immutable after creation (thread-safe to share), one plan per device.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns GTC_E_CUDA.
+ */
+#ifndef GTC_H_
+#define GTC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTC_VERSION 100
+
+#define GTC_OK          0
+#define GTC_E_ARG      -1   /* invalid argument                      */
+#define GTC_E_CUDA     -2   /* CUDA runtime / driver error           */
+#define GTC_E_NOMEM    -3   /* workspace too small / allocation      */
+#define GTC_E_UNSUP    -4   /* unsupported configuration             */
+
+/* GEMM engines for the segment operator contraction */
+#define GTC_GEMM_TCGEN05_3XTF32  0   /* TMA + tcgen05.mma kind::tf32, hi/lo split, fp32 TMEM accumulators (default) */
+#define GTC_GEMM_SIMT_FP32       1   /* CUDA-core fp32 FMA tiles (validation engine for the tensor-core path)       */
+
+/* patch modes */
+#define GTC_PATCH_VIT  0   /* ViT_dataloader.py:31-51  : (x+120)/120, clip, bicubic, 3 identical channels            */
+#define GTC_PATCH_CNN  1   /* my_dataloader.py:17-21   : grey picture (top row = highest bin), bilinear, ImageNet normalise */
+
+typedef struct gtc_plan gtc_plan;
+typedef void* gtc_stream_t;
+
+int         gtc_version(void);
+const char* gtc_last_error(void);
+/* sm count, compute capability and memory of `device`; any out pointer may be NULL. */
+int         gtc_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * CQT of fixed-length segments  -- replaces librosa.cqt + np.abs()**4 + librosa.amplitude_to_db(ref=np.amax)
+ * + cqt_lim at /root/reference/cqt.py:55-58 (and new_cqt.py:25-30, tablature-generator (1).py:326-331).
+ *
+ * For a fixed segment length the whole librosa.cqt call is a linear map; the host designs it once
+ * (gtc_b200/cqt_design.py) and hands it over as `h_operator`:
+ *      h_operator[(t*n_bins + bin)*2 + c][j],  c = 0 real / 1 imag, j = 0..seg_len-1   (row-major, fp32)
+ * ------------------------------------------------------------------------------------------------------------ */
+int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int seg_hop, int n_bins, int n_frames,
+                        const float* h_operator, int gemm_engine);
+int gtc_cqt_plan_destroy(gtc_plan* plan);
+/* number of operator rows sharing one audio row (P = seg_len/seg_hop when it divides, else 1) */
+int gtc_cqt_plan_parts(const gtc_plan* plan);
+/* bytes of scratch gtc_cqt_segments_db needs for `n_seg` segments spread over `n_clips` clips */
+int gtc_cqt_workspace_bytes(const gtc_plan* plan, int64_t n_seg, int64_t n_clips, size_t* bytes);
+
+/*
+ * All clips of a shard concatenated in d_audio (mono fp32).  d_clip_off[n_clips+1]: sample offset of each clip;
+ * d_seg_off[n_clips+1]: index of each clip's first segment in the output; segment s of clip c covers samples
+ * [d_clip_off[c] + s*seg_hop, +seg_len)  (window arithmetic of cqt.py:26-45; the caller computes the counts).
+ * d_out_db: [n_seg, n_bins, n_frames] fp32, C-order  == np.stack of the arrays cqt.py:58 produces.
+ * power: exponent applied to |C| (4 at cqt.py:56; 1 at tablature_generator.py:620); amin/top_db as librosa;
+ * values < cut_db are replaced by floor_db (cqt_lim: -60 -> -120); pass cut_db = -INFINITY to disable.
+ */
+int gtc_cqt_segments_db(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off,
+                        const int64_t* d_seg_off, int64_t n_clips, int64_t n_seg, float* d_out_db,
+                        void* d_workspace, size_t workspace_bytes,
+                        float power, float amin, float top_db, float cut_db, float floor_db,
+                        gtc_stream_t stream);
+/* Same contraction, complex output before |.|: d_out_c [n_seg, n_bins, n_frames, 2] fp32 (== librosa.cqt). */
+int gtc_cqt_segments_complex(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off,
+                             const int64_t* d_seg_off, int64_t n_clips, int64_t n_seg, float* d_out_c,
+                             void* d_workspace, size_t workspace_bytes, gtc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Label rasterisation -- replaces GuitarTablatureExtractor.extract_tablature_from_jams + midi_to_tablature +
+ * extract_tablature_from_pitch_contour and the stats of process_file (/root/reference/jam_to_tablature.py:55-178,
+ * 303-331).  Bit-exact integer output.
+ *
+ * note events of clip c: indices [d_evt_off[c], d_evt_off[c+1]) of d_onset/d_dur/d_pitch (fp64, as JAMS stores them)
+ * contour observations : indices [d_con_off[c], d_con_off[c+1]) of d_con_time/d_con_midi/d_con_conf/d_con_kind
+ *                        (d_con_midi = librosa.hz_to_midi(frequency) computed by the host in fp64; kind 1 marks an
+ *                        observation whose confidence is None -- the reference raises on it and keeps zeros).
+ *                        All contour pointers may be NULL (no fallback data).
+ * d_seg_time[n_seg]    : fp64 segment times (jam_to_tablature.py:273-274), d_seg_off as above.
+ * d_out [n_seg,6,19] int8 multi-hot; d_stats[3] += {total, with_notes, with_first_string} (int64, caller zeroes).
+ * ------------------------------------------------------------------------------------------------------------ */
+int gtc_rasterize_tabs(const double* d_onset, const double* d_dur, const double* d_pitch, const int64_t* d_evt_off,
+                       const double* d_con_time, const double* d_con_midi, const double* d_con_conf,
+                       const int8_t* d_con_kind, const int64_t* d_con_off,
+                       const double* d_seg_time, const int64_t* d_seg_off, int64_t n_clips, int64_t n_seg,
+                       int8_t* d_out, int64_t* d_stats, gtc_stream_t stream);
+
+/* my_dataloader.py:40-44 : (n,6,19) int8 -> (n,6) int64 argmax (first 1 wins; all-zero row -> 0). */
+int gtc_labels_argmax(const int8_t* d_tabs, int64_t n, int64_t* d_out, gtc_stream_t stream);
+/* ViT_dataloader.py:54 + default collate: (n,6,19) int8 -> six contiguous (n,19) int64 heads: d_out[6][n][19]. */
+int gtc_labels_vit_heads(const int8_t* d_tabs, int64_t n, int64_t* d_out, gtc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Patch assembly -- replaces GuitarTabDataset.__getitem__ + default collate of
+ * /root/reference/ViT_dataloader.py:27-51 (mode VIT) and the tensor contract of my_dataloader.py:17-21 (mode CNN).
+ * d_db [n_total, n_bins, n_frames] fp32 dB features; d_index[n] (may be NULL = identity) selects and orders the
+ * items of the batch (the DataLoader's sampler); d_out [n, 3, out_h, out_w] fp32.
+ * ------------------------------------------------------------------------------------------------------------ */
+int gtc_patches(const float* d_db, const int64_t* d_index, int64_t n, int n_bins, int n_frames,
+                int out_h, int out_w, int mode, float* d_out, gtc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTC_H_ */
