@@ -111,9 +111,11 @@ rasterize_kernel(const double* __restrict__ onset, const double* __restrict__ du
 }
 
 // my_dataloader.py:40-41 : np.argmax(annotation, axis=1)
-__global__ void argmax_kernel(const int8_t* __restrict__ tabs, int64_t n_rows /* n*6 */, int64_t* __restrict__ out) {
+__global__ void argmax_kernel(const int8_t* __restrict__ tabs, const int64_t* __restrict__ index, int64_t n_rows /* n*6 */,
+                              int64_t* __restrict__ out) {
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
-    const int8_t* row = tabs + r * kFrets;
+    const int64_t item = r / kStrings, s = r - item * kStrings;
+    const int8_t* row = tabs + ((index ? index[item] : item) * kStrings + s) * kFrets;
     int best = 0;
     int8_t bv = row[0];
 #pragma unroll
@@ -126,14 +128,15 @@ __global__ void argmax_kernel(const int8_t* __restrict__ tabs, int64_t n_rows /*
 }
 
 // ViT_dataloader.py:28,54 + collate : heads[s][i][f] = (int64) tabs[i][s][f]
-__global__ void vit_heads_kernel(const int8_t* __restrict__ tabs, int64_t n, int64_t* __restrict__ out) {
+__global__ void vit_heads_kernel(const int8_t* __restrict__ tabs, const int64_t* __restrict__ index, int64_t n,
+                                 int64_t* __restrict__ out) {
   const int64_t total = n * kTabBytes;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = j / (n * kFrets);
     const int64_t rem = j - s * n * kFrets;
     const int64_t i = rem / kFrets;
     const int64_t f = rem - i * kFrets;
-    out[j] = (int64_t)tabs[(i * kStrings + s) * kFrets + f];
+    out[j] = (int64_t)tabs[((index ? index[i] : i) * kStrings + s) * kFrets + f];
   }
 }
 
@@ -150,9 +153,7 @@ extern "C" int gtc_rasterize_tabs(const double* d_onset, const double* d_dur, co
   if (n_seg == 0) return GTC_OK;
   GTC_REQUIRE(n_clips > 0 && n_clips < (1 << 30), GTC_E_ARG, "gtc_rasterize_tabs: n_clips out of range");
   GTC_REQUIRE(d_evt_off && d_seg_time && d_seg_off && d_out && d_stats, GTC_E_ARG, "gtc_rasterize_tabs: null pointer");
-  const bool has_con = d_con_off != nullptr;
-  GTC_REQUIRE(!has_con || (d_con_time && d_con_midi && d_con_conf && d_con_kind), GTC_E_ARG,
-              "gtc_rasterize_tabs: contour offsets given without contour arrays");
+  // contour arrays may be NULL when every clip's contour range is empty (nothing is dereferenced then)
   const int threads = 256, wpb = threads / 32;
   int sms = sm_count_of_current_device();
   if (sms <= 0) return GTC_E_CUDA;
@@ -165,7 +166,8 @@ extern "C" int gtc_rasterize_tabs(const double* d_onset, const double* d_dur, co
   return GTC_OK;
 }
 
-extern "C" int gtc_labels_argmax(const int8_t* d_tabs, int64_t n, int64_t* d_out, gtc_stream_t stream) {
+extern "C" int gtc_labels_argmax(const int8_t* d_tabs, const int64_t* d_index, int64_t n, int64_t* d_out,
+                                 gtc_stream_t stream) {
   GTC_REQUIRE(n >= 0, GTC_E_ARG, "gtc_labels_argmax: negative n");
   if (n == 0) return GTC_OK;
   GTC_REQUIRE(d_tabs && d_out, GTC_E_ARG, "gtc_labels_argmax: null pointer");
@@ -173,12 +175,13 @@ extern "C" int gtc_labels_argmax(const int8_t* d_tabs, int64_t n, int64_t* d_out
   if (sms <= 0) return GTC_E_CUDA;
   int64_t blocks = ceil_div(n * 6, 256);
   if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
-  argmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_tabs, n * 6, d_out);
+  argmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_tabs, d_index, n * 6, d_out);
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;
 }
 
-extern "C" int gtc_labels_vit_heads(const int8_t* d_tabs, int64_t n, int64_t* d_out, gtc_stream_t stream) {
+extern "C" int gtc_labels_vit_heads(const int8_t* d_tabs, const int64_t* d_index, int64_t n, int64_t* d_out,
+                                    gtc_stream_t stream) {
   GTC_REQUIRE(n >= 0, GTC_E_ARG, "gtc_labels_vit_heads: negative n");
   if (n == 0) return GTC_OK;
   GTC_REQUIRE(d_tabs && d_out, GTC_E_ARG, "gtc_labels_vit_heads: null pointer");
@@ -186,7 +189,7 @@ extern "C" int gtc_labels_vit_heads(const int8_t* d_tabs, int64_t n, int64_t* d_
   if (sms <= 0) return GTC_E_CUDA;
   int64_t blocks = ceil_div(n * 114, 256);
   if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
-  vit_heads_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_tabs, n, d_out);
+  vit_heads_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_tabs, d_index, n, d_out);
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;
 }

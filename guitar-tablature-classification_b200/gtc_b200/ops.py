@@ -1,0 +1,172 @@
+"""Torch-facing wrappers over the C ABI: device tensors in, device tensors out, everything on the current stream.
+
+PyTorch is used here only for device memory and streams (plumbing); all arithmetic runs in libgtc.so's kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .cqt_design import CqtRecipe, get_operator, n_frames_of
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.GtcError("libgtc kernels take CUDA tensors only (there is no CPU fallback)")
+        if t is not None and not t.is_contiguous():
+            raise _lib.GtcError("libgtc kernels take contiguous tensors")
+
+
+def segment_counts(clip_lens: Sequence[int], seg_len: int, seg_hop: int) -> np.ndarray:
+    """cqt.py:30 -- number of complete windows per clip (never negative)."""
+    n = np.asarray(clip_lens, dtype=np.int64)
+    return np.maximum(0, (n - seg_len) // seg_hop + 1)
+
+
+class CqtPlan:
+    """Device-resident segment operator for one recipe (replaces the per-call basis rebuild of librosa.cqt)."""
+
+    def __init__(self, recipe: CqtRecipe = CqtRecipe(), device: Optional[int] = None, engine: Optional[int] = None,
+                 seg_len: Optional[int] = None, seg_hop: Optional[int] = None):
+        lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.GtcError("CqtPlan needs a CUDA device (there is no CPU fallback)")
+        self.recipe = recipe
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.seg_len = recipe.seg_len if seg_len is None else int(seg_len)
+        self.seg_hop = recipe.seg_hop if seg_hop is None else int(seg_hop)
+        self.n_bins = recipe.n_bins
+        self.n_frames = n_frames_of(recipe, self.seg_len)
+        self.engine = _lib.GTC_GEMM_TCGEN05_3XTF32 if engine is None else int(engine)
+        op = np.ascontiguousarray(get_operator(recipe, self.seg_len), dtype=np.float32)
+        assert op.shape == (2 * self.n_bins * self.n_frames, self.seg_len)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.gtc_cqt_plan_create(C.byref(handle), self.device, self.seg_len, self.seg_hop, self.n_bins,
+                                               self.n_frames, op.ctypes.data_as(C.c_void_p), self.engine),
+                       "gtc_cqt_plan_create")
+        self._h = handle
+        self._ws: Optional[torch.Tensor] = None
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _lib.load().gtc_cqt_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def workspace(self, n_seg: int, n_clips: int) -> torch.Tensor:
+        need = C.c_size_t()
+        _lib.check(_lib.load().gtc_cqt_workspace_bytes(self._h, n_seg, n_clips, C.byref(need)), "gtc_cqt_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need.value:
+            self._ws = None
+            self._ws = torch.empty(need.value, dtype=torch.uint8, device=f"cuda:{self.device}")
+        return self._ws
+
+    def offsets(self, clip_lens: Sequence[int]):
+        """Host-side window arithmetic (cqt.py:26-30): (clip_off, seg_off) int64 arrays of n_clips+1 entries."""
+        lens = np.asarray(clip_lens, dtype=np.int64)
+        clip_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        seg_off = np.concatenate([[0], np.cumsum(segment_counts(lens, self.seg_len, self.seg_hop))]).astype(np.int64)
+        return clip_off, seg_off
+
+    def segments_db(self, audio: torch.Tensor, clip_off: torch.Tensor, seg_off: torch.Tensor, n_seg: int,
+                    out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """audio: concatenated mono fp32 clips (device); returns [n_seg, n_bins, T] fp32 dB features
+        (== np.stack of what cqt.py:58 saves per segment)."""
+        _need_cuda(audio, clip_off, seg_off)
+        assert audio.dtype == torch.float32 and clip_off.dtype == torch.int64 and seg_off.dtype == torch.int64
+        n_clips = clip_off.numel() - 1
+        if out is None:
+            out = torch.empty((n_seg, self.n_bins, self.n_frames), dtype=torch.float32, device=audio.device)
+        ws = self.workspace(n_seg, n_clips) if workspace is None else workspace
+        r = self.recipe
+        _lib.check(_lib.load().gtc_cqt_segments_db(self._h, _ptr(audio), _ptr(clip_off), _ptr(seg_off), n_clips, n_seg,
+                                                   _ptr(out), _ptr(ws), ws.numel(), r.power, r.amin, r.top_db, r.cut_db,
+                                                   r.floor_db, _stream()), "gtc_cqt_segments_db")
+        return out
+
+    def segments_complex(self, audio: torch.Tensor, clip_off: torch.Tensor, seg_off: torch.Tensor, n_seg: int) -> torch.Tensor:
+        """[n_seg, n_bins, T] complex64 (== librosa.cqt of every segment)."""
+        _need_cuda(audio, clip_off, seg_off)
+        n_clips = clip_off.numel() - 1
+        out = torch.empty((n_seg, self.n_bins, self.n_frames, 2), dtype=torch.float32, device=audio.device)
+        ws = self.workspace(n_seg, n_clips)
+        _lib.check(_lib.load().gtc_cqt_segments_complex(self._h, _ptr(audio), _ptr(clip_off), _ptr(seg_off), n_clips, n_seg,
+                                                        _ptr(out), _ptr(ws), ws.numel(), _stream()), "gtc_cqt_segments_complex")
+        return torch.view_as_complex(out)
+
+
+def rasterize_tabs(onset, dur, pitch, evt_off, seg_time, seg_off, contour=None, stats: Optional[torch.Tensor] = None):
+    """Device label rasteriser.  onset/dur/pitch fp64 [n_evt], evt_off int64 [n_clips+1], seg_time fp64 [n_seg],
+    seg_off int64 [n_clips+1]; contour = (time, midi, conf, kind, off) or None.
+    Returns (labels int8 [n_seg,6,19], stats int64 [3] = total, with_notes, with_first_string)."""
+    _need_cuda(onset, dur, pitch, evt_off, seg_time, seg_off)
+    n_seg = seg_time.numel()
+    n_clips = seg_off.numel() - 1
+    out = torch.empty((n_seg, 6, 19), dtype=torch.int8, device=seg_time.device)
+    if stats is None:
+        stats = torch.zeros(3, dtype=torch.int64, device=seg_time.device)
+    ct = cm = cc = ck = co = None
+    if contour is not None:
+        ct, cm, cc, ck, co = contour
+        _need_cuda(ct, cm, cc, ck, co)
+        assert ck.dtype == torch.int8 and co.dtype == torch.int64
+    _lib.check(_lib.load().gtc_rasterize_tabs(_ptr(onset), _ptr(dur), _ptr(pitch), _ptr(evt_off), _ptr(ct), _ptr(cm),
+                                              _ptr(cc), _ptr(ck), _ptr(co), _ptr(seg_time), _ptr(seg_off), n_clips, n_seg,
+                                              _ptr(out), _ptr(stats), _stream()), "gtc_rasterize_tabs")
+    return out, stats
+
+
+def labels_argmax(tabs: torch.Tensor, index: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(n_total,6,19) int8 [+ index] -> (n,6) int64 (my_dataloader.py:40-44)."""
+    _need_cuda(tabs, index)
+    assert tabs.dtype == torch.int8 and (index is None or index.dtype == torch.int64)
+    n = tabs.shape[0] if index is None else index.numel()
+    out = torch.empty((n, 6), dtype=torch.int64, device=tabs.device)
+    _lib.check(_lib.load().gtc_labels_argmax(_ptr(tabs), _ptr(index), n, _ptr(out), _stream()), "gtc_labels_argmax")
+    return out
+
+
+def labels_vit_heads(tabs: torch.Tensor, index: Optional[torch.Tensor] = None):
+    """(n_total,6,19) int8 [+ index] -> list of six (n,19) int64 tensors (ViT_dataloader.py:54 after default collate)."""
+    _need_cuda(tabs, index)
+    assert tabs.dtype == torch.int8 and (index is None or index.dtype == torch.int64)
+    n = tabs.shape[0] if index is None else index.numel()
+    out = torch.empty((6, n, 19), dtype=torch.int64, device=tabs.device)
+    _lib.check(_lib.load().gtc_labels_vit_heads(_ptr(tabs), _ptr(index), n, _ptr(out), _stream()), "gtc_labels_vit_heads")
+    return [out[i] for i in range(6)]
+
+
+def patches(db: torch.Tensor, index: Optional[torch.Tensor] = None, img_size=(224, 224), mode: int = _lib.GTC_PATCH_VIT,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """db [n_total, n_bins, T] fp32 dB features -> [n, 3, H, W] fp32 patches (ViT or CNN contract)."""
+    _need_cuda(db, index)
+    assert db.dtype == torch.float32 and db.dim() == 3
+    n = db.shape[0] if index is None else index.numel()
+    if index is not None:
+        assert index.dtype == torch.int64
+    h, w = int(img_size[0]), int(img_size[1])
+    if out is None:
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=db.device)
+    _lib.check(_lib.load().gtc_patches(_ptr(db), _ptr(index), n, db.shape[1], db.shape[2], h, w, int(mode), _ptr(out),
+                                       _stream()), "gtc_patches")
+    return out

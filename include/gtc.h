@@ -103,10 +103,11 @@ int gtc_rasterize_tabs(const double* d_onset, const double* d_dur, const double*
                        const double* d_seg_time, const int64_t* d_seg_off, int64_t n_clips, int64_t n_seg,
                        int8_t* d_out, int64_t* d_stats, gtc_stream_t stream);
 
-/* my_dataloader.py:40-44 : (n,6,19) int8 -> (n,6) int64 argmax (first 1 wins; all-zero row -> 0). */
-int gtc_labels_argmax(const int8_t* d_tabs, int64_t n, int64_t* d_out, gtc_stream_t stream);
-/* ViT_dataloader.py:54 + default collate: (n,6,19) int8 -> six contiguous (n,19) int64 heads: d_out[6][n][19]. */
-int gtc_labels_vit_heads(const int8_t* d_tabs, int64_t n, int64_t* d_out, gtc_stream_t stream);
+/* d_index[n] (may be NULL = identity) selects and orders the batch items out of d_tabs [n_total,6,19].
+ * my_dataloader.py:40-44 : int8 (6,19) -> int64 (6,) argmax (first 1 wins; all-zero row -> 0); d_out [n,6]. */
+int gtc_labels_argmax(const int8_t* d_tabs, const int64_t* d_index, int64_t n, int64_t* d_out, gtc_stream_t stream);
+/* ViT_dataloader.py:54 + default collate: six contiguous (n,19) int64 heads: d_out[6][n][19]. */
+int gtc_labels_vit_heads(const int8_t* d_tabs, const int64_t* d_index, int64_t n, int64_t* d_out, gtc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Patch assembly -- replaces GuitarTabDataset.__getitem__ + default collate of
