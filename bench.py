@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- seconds-of-audio/sec of the hot path (CQT + dB, labels, patches) on N B200s, one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (default N=1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (restated oracle)
+
+A "step" is one pass of the hot path over BASELINE.json configs[1]: 360 synthetic clips x 30 s @ 22.05 kHz mono
+(107 640 segments) per GPU (weak scaling).  `value` = kernel-only throughput with inputs resident in HBM;
+`e2e` = the same through the public FrontEnd API with pinned HOST inputs (audio + events H2D, features + labels D2H in
+the timed region; patches stay on the device because the training engines consume them there).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.join(ROOT, "guitar-tablature-classification_b200")
+for _p in (ROOT, PKG_ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "seconds-of-audio/sec CQT+labels+patches"
+UNIT = "s_audio/s"
+SR = 22050
+N_CLIPS = 360
+CLIP_SECONDS = 30.0
+ALGO_BYTES_PER_S_AUDIO = 88200 + 19200 + 1600 + 19200 + 6021120          # SURVEY.md 8d / BASELINE.md section 4
+PATCH_BYTES_PER_SEGMENT = 3 * 224 * 224 * 4 + 96 * 5 * 4                  # written + read per segment by the patch kernel
+
+
+def workload_config(n_clips=N_CLIPS):
+    n = int(SR * CLIP_SECONDS)
+    segs = (n - 4410) // 2205 + 1
+    return {"workload": "BASELINE.json configs[1]: GuitarSet-shaped batch, %d synthetic clips x %.0f s @ 22.05 kHz mono -> "
+                        "cqt.py CQT+|.|^4+dB+cut, jam_to_tablature labels, ViT_dataloader (3,224,224) patches" % (n_clips, CLIP_SECONDS),
+            "clips_per_gpu": n_clips, "segments_per_gpu": n_clips * segs, "sr": SR, "seg_len": 4410, "seg_hop": 2205,
+            "n_bins": 96, "frames": 5, "patch": [3, 224, 224],
+            "cache": "per-step inputs (0.95 GB audio) and outputs (65 GB of patches through a 5 GB ring) exceed the 126 MB L2; no flush needed"}
+
+
+# ======================================================================================================================
+# CPU reference arm: the reference's control flow (cqt.py loop, jam_to_tablature.process_file loop,
+# ViT_dataloader.__getitem__) executed with the restated oracle -- librosa/soxr/jams are not installable here.
+# ======================================================================================================================
+
+def _cpu_clip_job(args):
+    """One clip through the reference's three scripts, file I/O on tmpfs included."""
+    seed, n_samples, outdir = args
+    import torch
+    torch.set_num_threads(1)
+    from oracle import cqt_oracle, labels_oracle, patches_oracle
+    rng = np.random.default_rng(seed)
+    t = np.arange(n_samples) / SR
+    y = 0.003 * rng.standard_normal(n_samples)
+    for _ in range(int(6 * n_samples / SR)):
+        f = 440.0 * 2 ** ((rng.uniform(40, 82) - 69) / 12)
+        on = rng.uniform(0, n_samples / SR)
+        rel = np.maximum(t - on, 0)
+        y += rng.uniform(0.3, 1.0) * np.where(t >= on, np.exp(-rel / 0.4), 0.0) * np.sin(2 * np.pi * f * rel)
+    y = (0.5 * y / np.abs(y).max()).astype(np.float32)
+    dur = n_samples / SR
+    notes = []
+    for s in range(6):
+        for _ in range(rng.poisson(3 * dur)):
+            notes.append(labels_oracle.Observation(rng.uniform(0, dur), float(np.clip(rng.exponential(0.4), 0.05, 4)),
+                                                   [40, 45, 50, 55, 59, 64][s] + int(rng.integers(0, 19)) + rng.normal(0, 0.15)))
+    jam = labels_oracle.Jam([labels_oracle.Annotation('note_midi', notes)])
+    t0 = time.perf_counter()
+    feats = cqt_oracle.process_clip(y, SR)                                   # cqt.py:19-65 (basis rebuilt per call, like librosa)
+    for k, f in enumerate(feats):
+        np.save(os.path.join(outdir, f"clip{seed}_segment_{k}.npy"), np.asfortranarray(f))
+    times = labels_oracle.segment_times(dur, len(feats))                     # jam_to_tablature.py:259-274
+    tabs, _ = labels_oracle.process_segments(jam, times)
+    for i, tab in enumerate(tabs):
+        np.save(os.path.join(outdir, f"clip{seed}_{i:04d}.npy"), tab)
+    for k in range(len(feats)):                                              # ViT_dataloader.py:22-56
+        a = np.load(os.path.join(outdir, f"clip{seed}_segment_{k}.npy"))
+        lab = np.load(os.path.join(outdir, f"clip{seed}_{k:04d}.npy")).astype(np.float32)
+        patches_oracle.vit_patch_torch(a)
+        [lab[i].astype(np.int64) for i in range(6)]
+    return dur, time.perf_counter() - t0
+
+
+def cpu_reference_pass(clips: int, clip_seconds: float, workers: int, seed0: int = 0):
+    """ProcessPoolExecutor fan-out over clips as new_cqt.py:53-61 does.  Returns (audio seconds, seconds of work):
+    the jobs run concurrently (one per worker per round) and each reports its own busy time, so interpreter start-up
+    and imports are excluded while memory-bandwidth contention between the workers is included."""
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    outdir = tempfile.mkdtemp(prefix="gtc_cpu_", dir=base)
+    try:
+        jobs = [(seed0 + i, int(SR * clip_seconds), outdir) for i in range(clips)]
+        if workers <= 1:
+            res = [_cpu_clip_job(j) for j in jobs]
+        else:
+            with ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("fork")) as ex:
+                res = list(ex.map(_cpu_clip_job, jobs))
+        rounds = -(-clips // max(1, workers))
+        wall = rounds * max(r[1] for r in res) if workers > 1 else sum(r[1] for r in res)
+        return sum(r[0] for r in res), wall
+    finally:
+        shutil.rmtree(outdir, ignore_errors=True)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    workers = max(1, cores)
+    clip_s = 10.0                                       # bounded sample: `workers` clips x 10 s per step
+    for _ in range(args.warmup):
+        cpu_reference_pass(min(workers, 2), 2.0, min(workers, 2))
+    t_audio = t_wall = 0.0
+    for s in range(args.steps):
+        a, w = cpu_reference_pass(workers, clip_s, workers, seed0=1000 * s)
+        t_audio += a
+        t_wall += w
+    value = t_audio / t_wall
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_wall / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                             "sample": f"{workers} clips x {clip_s:.0f} s per step on {workers} processes "
+                                       "(restated NumPy/SciPy oracle of cqt.py + jam_to_tablature.py + ViT_dataloader.py, "
+                                       ".npy I/O on tmpfs; librosa/soxr/jams are not installable, so this is a port, not librosa)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ======================================================================================================================
+# CUDA arm
+# ======================================================================================================================
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML, in-process thread)."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+               0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def run_cuda_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        workers = max(1, min(cores, 16))
+        a, w = cpu_reference_pass(workers, 10.0, workers)
+        cpu_baseline = {"value": a / w, "unit": UNIT, "cores": workers, "kind": "port",
+                        "sample": f"{workers} clips x 10 s, one process per core ({cores} host cores), restated reference "
+                                  "(cqt.py + jam_to_tablature.py + ViT_dataloader.py loops on the NumPy/SciPy oracle, .npy I/O on tmpfs); "
+                                  "not librosa -- it is not installable here"}
+
+    import torch
+    import torch.distributed as dist
+    from gtc_b200 import CqtRecipe, synth, shard
+    from gtc_b200.pipeline import FrontEnd, ShardInputs
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: this framework has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+
+    recipe = CqtRecipe()
+    n_clips = args.clips
+    n = int(SR * CLIP_SECONDS)
+    # synthetic shard of this rank (clip ids rank, rank+world, ... of a 360*world-clip corpus): weak scaling
+    audio_dev = synth.pluck_clips(n_clips, n, sr=SR, seed=1 + rank, device=dev, block=24).reshape(-1)
+    on, du, pi, evt_off = synth.note_events([CLIP_SECONDS] * n_clips, seed=2 + rank)
+    events_host = torch.from_numpy(np.stack([on, du, pi])).pin_memory()
+    events_dev = events_host.to(dev)
+    audio_host = torch.empty(audio_dev.shape, dtype=torch.float32, pin_memory=True)
+    audio_host.copy_(audio_dev)
+    lens = np.full(n_clips, n, dtype=np.int64)
+    fe = FrontEnd(recipe, device=local_rank, chunk_segments=args.chunk_segments, patch_batch=args.patch_batch)
+    inp_dev = ShardInputs(audio_dev, lens, events_dev, evt_off, sr=SR)
+    inp_host = ShardInputs(audio_host, lens, events_host, evt_off, sr=SR)
+    chunks = fe.plan_chunks(inp_dev)
+    seconds_per_step = n_clips * CLIP_SECONDS
+    stats_vec = torch.zeros(8, dtype=torch.int64, device=dev)
+
+    def step(inp, device_inputs):
+        out = fe.run(inp, device_inputs=device_inputs, chunks=chunks)
+        # tiny per-shard stats gather (the path's only collective), jam_to_tablature.py:376-378
+        stats_vec[0] = n_clips
+        stats_vec[1] = out.n_seg
+        stats_vec[2] = int(lens.sum())
+        stats_vec[3:6] = fe._last_stats[0]
+        if world > 1:
+            shard.gather_stats(stats_vec)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(inp, device_inputs, steps, warmup):
+        for _ in range(warmup):
+            step(inp, device_inputs)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = step(inp, device_inputs)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    with ClockSampler(physical_gpu_index(local_rank)) as clocks:
+        ms_dev, out_dev = timed(inp_dev, True, args.steps, args.warmup)
+    ms_e2e, out_e2e = timed(inp_host, False, args.steps, args.warmup)
+
+    # dominant kernel (patch store stream) timed live, per launch, on its own stream
+    n_seg = out_dev.n_seg
+    pb = min(args.patch_batch, n_seg)
+    db_all = fe._bufs[("db_all", False)][: n_seg * 480].view(n_seg, 96, 5)
+    ring = fe._bufs[("patch0", False)][: pb * 3 * 224 * 224].view(pb, 3, 224, 224)
+    from gtc_b200 import ops
+    evs = []
+    torch.cuda.synchronize()
+    with torch.cuda.stream(fe.s_comp):
+        for _ in range(2):
+            ops.patches(db_all[:pb], out=ring)
+        for i in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(fe.s_comp)
+            ops.patches(db_all[(i * pb) % max(1, n_seg - pb + 1):][:pb], out=ring)
+            b.record(fe.s_comp)
+            evs.append((a, b))
+    torch.cuda.synchronize()
+    patch_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+    value = world * seconds_per_step * args.steps / (ms_dev * 1e-3)
+    e2e_value = world * seconds_per_step * args.steps / (ms_e2e * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = pb * PATCH_BYTES_PER_SEGMENT / (patch_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "patch_kernel_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(n_clips),
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": out_e2e.h2d_bytes, "d2h_bytes_per_step": out_e2e.d2h_bytes,
+                        "note": "pinned host audio+events in, dB features + labels + stats back; patches stay in HBM for the engines"},
+                "gpu_launches": out_dev.launches * args.steps,
+                "roofline": {"bound": "hbm", "kernel": "patch_kernel<5> (gtc_patches)", "achieved": achieved, "peak": peak_hbm,
+                             "unit": "GB/s", "frac": achieved / peak_hbm, "traffic": traffic,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                             "launch_ms": patch_ms, "segments_per_launch": pb},
+                "path_roofline": {"algorithmic_bytes_per_s_audio": ALGO_BYTES_PER_S_AUDIO,
+                                  "frac_of_hbm_peak": (value / world) * ALGO_BYTES_PER_S_AUDIO / (peak_hbm * 1e9)},
+                "cpu_baseline": cpu_baseline,
+                "clocks": clocks.summary()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--clips", type=int, default=N_CLIPS)
+    ap.add_argument("--chunk-segments", type=int, default=16384)
+    ap.add_argument("--patch-batch", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_cuda_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,5 +1,6 @@
 // C-ABI entry points of the segment CQT (plan, workspace, frame -> GEMM -> finish) and library-wide helpers.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <math.h>
 #include <new>
 #include <vector>
@@ -106,6 +107,7 @@ extern "C" int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int 
   p.n_pad = (int)round_up(p.n_out, 128);
   p.engine = gemm_engine;
   p.sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("GTC_TC_KSPLIT")) p.tc_kb_per_split = atoi(e);
   if (gemm_engine == GTC_GEMM_TCGEN05_3XTF32 && (p.n_out % 16 != 0)) {
     delete plan;
     set_error("gtc_cqt_plan_create: tcgen05 engine needs 2*n_bins*n_frames %% 16 == 0 (got %d)", p.n_out);

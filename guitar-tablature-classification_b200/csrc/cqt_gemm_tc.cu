@@ -26,10 +26,12 @@ constexpr uint32_t X_TILE_BYTES = TBM * TBK * 4;        // 16 KB
 constexpr uint32_t OP_TILE_BYTES = TMAXN * TBK * 4;     // 32 KB (NC rows used)
 constexpr uint32_t STAGE_BYTES = 2 * X_TILE_BYTES + 2 * OP_TILE_BYTES;   // 96 KB
 constexpr uint32_t TC_SMEM_BYTES = TSTAGES * STAGE_BYTES + 1024 /*align slack*/;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 struct TcParams {
   int nc;                // operator rows per tile
+  int kb_per_split;      // k-blocks accumulated inside the tensor core before an fp32 RN add in registers
   int n_chunks;          // tiles along N
   int n_out;             // valid operator rows
   int kb_per_part;       // kp / 32
@@ -112,11 +114,25 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <bool kComplex>
+// tcgen05.ld of 8 columns (32x32b.x8)
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(addr) : "memory");
+}
+
+// NC = operator rows per tile (tcgen05.mma N).  Each of the 8 epilogue warps owns 32 rows x NC/2 columns and keeps
+// their running sums in registers: the tensor core adds into its TMEM accumulator with truncation (RZ), which over
+// the ~1650 accumulator updates of a full K pass biases the result by ~3e-5 relative -- measured on B200 -- so K is
+// cut into splits of `kb_per_split` k-blocks, each accumulated from zero in one of two TMEM stages and then summed
+// in fp32 (round-to-nearest) by the epilogue warps while the next split is already being multiplied.
+template <int NC, bool kComplex>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo,
                const TcParams prm) {
+  constexpr int H = NC / 2;                  // columns per epilogue warp
+  static_assert(NC % 16 == 0 && NC <= TMAXN && H % 8 == 0, "unsupported tile width");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bars[2 * TSTAGES + 4];
   __shared__ uint32_t s_tmem_slot;
@@ -137,7 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TSTAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&s_tmem_slot), 512);
@@ -147,8 +163,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   const uint32_t tmem_base = s_tmem_slot;
 
   const int nkb = prm.parts * prm.kb_per_part;
+  const int n_splits = (nkb + prm.kb_per_split - 1) / prm.kb_per_split;
   const int64_t n_tiles = prm.m_tiles * prm.n_chunks;
-  const uint32_t stage_tx = 2 * X_TILE_BYTES + 2 * (uint32_t)prm.nc * TBK * 4;
+  constexpr uint32_t stage_tx = 2 * X_TILE_BYTES + 2 * (uint32_t)NC * TBK * 4;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -162,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         const int64_t m_tile = tile / prm.n_chunks;
         const int chunk = (int)(tile - m_tile * prm.n_chunks);
         const int row0 = (int)(m_tile * TBM);
-        const int n0 = chunk * prm.nc;
+        const int n0 = chunk * NC;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(bar_empty(stage), phase ^ 1);
           mbar_expect_tx(bar_full(stage), stage_tx);
@@ -180,80 +197,94 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(TBM, prm.nc);
+      const uint32_t idesc = make_idesc_tf32(TBM, NC);
       int stage = 0; uint32_t phase = 0;
-      int64_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int acc = (int)(it & 1);
-        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-        mbar_wait(bar_tempty(acc), acc_phase ^ 1);         // epilogue drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)acc * TMAXN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(bar_full(stage), phase);
+      uint32_t it = 0;                                       // accumulator-stage use counter (one per K split)
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int kb = 0;
+        for (int sp = 0; sp < n_splits; ++sp, ++it) {
+          const int acc = (int)(it & 1u);
+          mbar_wait(bar_tempty(acc), ((it >> 1) & 1u) ^ 1u); // epilogue drained this accumulator stage
           tc_fence_after();
-          const uint64_t dxh = make_sw128_desc(st_xhi(stage)), dxl = make_sw128_desc(st_xlo(stage));
-          const uint64_t doh = make_sw128_desc(st_ohi(stage)), dol = make_sw128_desc(st_olo(stage));
+          const uint32_t tmem_d = tmem_base + (uint32_t)acc * TMAXN;
+          const int kb_end = min(nkb, kb + prm.kb_per_split);
+          for (int first = 1; kb < kb_end; ++kb, first = 0) {
+            mbar_wait(bar_full(stage), phase);
+            tc_fence_after();
+            const uint64_t dxh = make_sw128_desc(st_xhi(stage)), dxl = make_sw128_desc(st_xlo(stage));
+            const uint64_t doh = make_sw128_desc(st_ohi(stage)), dol = make_sw128_desc(st_olo(stage));
 #pragma unroll
-          for (int k = 0; k < TBK / TUMMA_K; ++k) {
-            const uint64_t adv = (uint64_t)((k * TUMMA_K * 4) >> 4);     // +32 B per k-step inside the swizzle row
-            umma_tf32(tmem_d, dxh + adv, doh + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_tf32(tmem_d, dxl + adv, doh + adv, idesc, 1u);
-            umma_tf32(tmem_d, dxh + adv, dol + adv, idesc, 1u);
+            for (int k = 0; k < TBK / TUMMA_K; ++k) {
+              const uint64_t adv = (uint64_t)((k * TUMMA_K * 4) >> 4);   // +32 B per k-step inside the swizzle row
+              umma_tf32(tmem_d, dxh + adv, doh + adv, idesc, (first && k == 0) ? 0u : 1u);
+              umma_tf32(tmem_d, dxl + adv, doh + adv, idesc, 1u);
+              umma_tf32(tmem_d, dxh + adv, dol + adv, idesc, 1u);
+            }
+            umma_commit(bar_empty(stage));                  // frees the smem slot when these MMAs retire
+            if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(bar_empty(stage));                    // frees the smem slot when these MMAs retire
-          if (kb == nkb - 1) umma_commit(bar_tfull(acc));   // accumulator complete
-          if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
+          umma_commit(bar_tfull(acc));                      // this split's partial sums are complete
         }
       }
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                        // which NC/2 column half
     const int n_mag = prm.n_out >> 1;
-    int64_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int acc = (int)(it & 1);
-      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t m_tile = tile / prm.n_chunks;
       const int chunk = (int)(tile - m_tile * prm.n_chunks);
       const int64_t row = m_tile * TBM + q * 32 + lane;
-      const int n0 = chunk * prm.nc;
-      mbar_wait(bar_tfull(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TMAXN;
-      float rmax = 0.f;
-      for (int c = 0; c < prm.nc; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c, r);
-        tmem_ld_wait();
-        const int n = n0 + c;
-        if (n < prm.n_out) {
-          if (kComplex) {
-            float4* dst = reinterpret_cast<float4*>(prm.cplx + row * prm.n_out + n);
+      const int n0 = chunk * NC + half * H;
+      float sum[H];
+      for (int sp = 0; sp < n_splits; ++sp, ++it) {
+        const int acc = (int)(it & 1u);
+        mbar_wait(bar_tfull(acc), (it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TMAXN + (uint32_t)(half * H);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-          } else {
-            float m[8];
+        for (int c = 0; c + 16 <= H; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c, r);
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float re = __uint_as_float(r[2 * j]), im = __uint_as_float(r[2 * j + 1]);
-              m[j] = re * re + im * im;
-              rmax = fmaxf(rmax, m[j]);
-            }
-            float4* dst = reinterpret_cast<float4*>(prm.mag2 + row * n_mag + (n >> 1));
-            dst[0] = make_float4(m[0], m[1], m[2], m[3]);
-            dst[1] = make_float4(m[4], m[5], m[6], m[7]);
+          for (int j = 0; j < 16; ++j) sum[c + j] = sp == 0 ? __uint_as_float(r[j]) : sum[c + j] + __uint_as_float(r[j]);
+        }
+        if (H % 16) {
+          constexpr int c = H - 8;
+          uint32_t r[8];
+          tmem_ld8(taddr + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sum[c + j] = sp == 0 ? __uint_as_float(r[j]) : sum[c + j] + __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty(acc));
+      }
+      // tile finished: |.|^2 + row max, or the raw complex values
+      if (kComplex) {
+#pragma unroll
+        for (int c = 0; c < H; c += 4)
+          if (n0 + c < prm.n_out)
+            *reinterpret_cast<float4*>(prm.cplx + row * prm.n_out + n0 + c) = make_float4(sum[c], sum[c + 1], sum[c + 2], sum[c + 3]);
+      } else {
+        float rmax = 0.f;
+#pragma unroll
+        for (int c = 0; c < H; c += 8) {
+          float m[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m[j] = sum[c + 2 * j] * sum[c + 2 * j] + sum[c + 2 * j + 1] * sum[c + 2 * j + 1];
+          if (n0 + c < prm.n_out) {
+            rmax = fmaxf(fmaxf(rmax, fmaxf(m[0], m[1])), fmaxf(m[2], m[3]));
+            *reinterpret_cast<float4*>(prm.mag2 + row * n_mag + ((n0 + c) >> 1)) = make_float4(m[0], m[1], m[2], m[3]);
           }
         }
+        atomicMax(reinterpret_cast<int*>(prm.rowmax + row), __float_as_int(rmax));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty(acc));
-      if (!kComplex) atomicMax(reinterpret_cast<int*>(prm.rowmax + row), __float_as_int(rmax));
     }
   }
 
@@ -299,10 +330,19 @@ static int encode_2d(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t
   return GTC_OK;
 }
 
+static const int kTileWidths[] = {256, 240, 192, 128, 64};
+
 static int pick_nc(int n_out) {
-  for (int nc = 256; nc >= 16; nc -= 16)
+  for (int nc : kTileWidths)
     if (n_out % nc == 0) return nc;
-  return 256;
+  return 256;                       // ragged: TMA zero-fills operator rows beyond n_pad, stores are guarded
+}
+
+template <int NC>
+static int set_smem_attr() {
+  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+  return GTC_OK;
 }
 
 int tc_plan_init(PlanImpl& p) {
@@ -314,14 +354,25 @@ int tc_plan_init(PlanImpl& p) {
   if (rc != GTC_OK) return rc;
   rc = encode_2d(&maps[1], p.d_op_lo, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)nc);
   if (rc != GTC_OK) return rc;
-  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-  return GTC_OK;
+  switch (nc) {
+    case 256: return set_smem_attr<256>();
+    case 240: return set_smem_attr<240>();
+    case 192: return set_smem_attr<192>();
+    case 128: return set_smem_attr<128>();
+    default: return set_smem_attr<64>();
+  }
 }
 
 void tc_plan_free(PlanImpl& p) {
   if (p.tmap_op_hi) delete[] reinterpret_cast<CUtensorMap*>(p.tmap_op_hi);
   p.tmap_op_hi = p.tmap_op_lo = nullptr;
+}
+
+template <int NC>
+static void launch_nc(bool cplx, unsigned grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b,
+                      const CUtensorMap& c, const CUtensorMap& d, const TcParams& prm) {
+  if (cplx) gemm_tc_kernel<NC, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, c, d, prm);
+  else      gemm_tc_kernel<NC, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, c, d, prm);
 }
 
 int launch_gemm_tc(const PlanImpl& p, const float* d_xhi, const float* d_xlo, int64_t n_rows_pad, int64_t n_rows_alloc,
@@ -334,6 +385,7 @@ int launch_gemm_tc(const PlanImpl& p, const float* d_xhi, const float* d_xlo, in
   if (rc != GTC_OK) return rc;
   TcParams prm;
   prm.nc = pick_nc(p.n_out);
+  prm.kb_per_split = p.tc_kb_per_split > 0 ? p.tc_kb_per_split : 12;
   prm.n_chunks = (int)ceil_div(p.n_out, prm.nc);
   prm.n_out = p.n_out;
   prm.kb_per_part = p.kp / TBK;
@@ -344,10 +396,14 @@ int launch_gemm_tc(const PlanImpl& p, const float* d_xhi, const float* d_xlo, in
   const unsigned grid = (unsigned)(n_tiles < p.sm_count ? n_tiles : p.sm_count);
   const CUtensorMap& tm_ohi = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_hi);
   const CUtensorMap& tm_olo = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_lo);
-  if (d_cplx)
-    gemm_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
-  else
-    gemm_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
+  const bool cplx = d_cplx != nullptr;
+  switch (prm.nc) {
+    case 256: launch_nc<256>(cplx, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
+    case 240: launch_nc<240>(cplx, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
+    case 192: launch_nc<192>(cplx, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
+    case 128: launch_nc<128>(cplx, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
+    default:  launch_nc<64>(cplx, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
+  }
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;
 }

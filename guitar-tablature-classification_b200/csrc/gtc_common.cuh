@@ -54,6 +54,7 @@ struct PlanImpl {
   int n_pad;        // n_out rounded up to 128
   int engine;
   int sm_count;
+  int tc_kb_per_split;  // K blocks per tensor-core accumulation split (0 = default), env GTC_TC_KSPLIT
   float* d_op;      // [n_pad][k_total]  operator, fp32, K padded per part (SIMT engine)
   float* d_op_hi;   // [n_pad][k_total]  tf32-representable high part (RN)
   float* d_op_lo;   // [n_pad][k_total]  residual  A - hi

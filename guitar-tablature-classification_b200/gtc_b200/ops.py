@@ -115,14 +115,17 @@ class CqtPlan:
         return torch.view_as_complex(out)
 
 
-def rasterize_tabs(onset, dur, pitch, evt_off, seg_time, seg_off, contour=None, stats: Optional[torch.Tensor] = None):
+def rasterize_tabs(onset, dur, pitch, evt_off, seg_time, seg_off, contour=None, stats: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None):
     """Device label rasteriser.  onset/dur/pitch fp64 [n_evt], evt_off int64 [n_clips+1], seg_time fp64 [n_seg],
     seg_off int64 [n_clips+1]; contour = (time, midi, conf, kind, off) or None.
     Returns (labels int8 [n_seg,6,19], stats int64 [3] = total, with_notes, with_first_string)."""
     _need_cuda(onset, dur, pitch, evt_off, seg_time, seg_off)
     n_seg = seg_time.numel()
     n_clips = seg_off.numel() - 1
-    out = torch.empty((n_seg, 6, 19), dtype=torch.int8, device=seg_time.device)
+    if out is None:
+        out = torch.empty((n_seg, 6, 19), dtype=torch.int8, device=seg_time.device)
+    assert out.dtype == torch.int8 and out.numel() == n_seg * 114 and out.is_contiguous()
     if stats is None:
         stats = torch.zeros(3, dtype=torch.int64, device=seg_time.device)
     ct = cm = cc = ck = co = None

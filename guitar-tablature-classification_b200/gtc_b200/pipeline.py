@@ -1,0 +1,237 @@
+"""Shard pipeline: audio + note events of many clips -> dB features, tablature labels and patch batches.
+
+This is the index-aligned in-memory path: clip ``c`` yields ``n_seg[c]`` feature segments
+(cqt.py:26-45), one label per segment at ``t_i = (i + 0.5) * duration / n_seg`` (jam_to_tablature.py:273-274 with
+``num_images = n_seg``) and one (3, H, W) patch per segment (ViT_dataloader.py:27-51 or the CNN contract).
+
+Clips are processed in chunks on three CUDA streams so that the host->device copy of chunk k+1 and the
+device->host copy of chunk k-1 overlap the kernels of chunk k.  With ``device_inputs=True`` the audio/events are
+already resident in HBM and no copies are issued (the kernel-only number of bench.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .cqt_design import CqtRecipe
+
+
+@dataclass
+class ShardInputs:
+    """One shard.  ``audio`` is the concatenation of all clips (fp32, 1-D): pinned host memory for the end-to-end
+    path or a CUDA tensor for the device-resident path.  Events are fp64 arrays concatenated per clip."""
+    audio: torch.Tensor            # [n_samples] fp32
+    clip_lens: np.ndarray          # [n_clips] int64 (host)
+    events: torch.Tensor           # [3, n_evt] fp64 rows = onset, duration, pitch (pinned host or CUDA, like audio)
+    evt_off: np.ndarray            # [n_clips+1] int64 (host)
+    sr: float = 22050.0
+
+
+@dataclass
+class ShardOutputs:
+    db: Optional[torch.Tensor] = None          # [n_seg, n_bins, T] fp32 (host pinned for e2e, device otherwise)
+    tabs: Optional[torch.Tensor] = None        # [n_seg, 6, 19] int8
+    stats: Optional[np.ndarray] = None         # total, with_notes, with_first_string
+    n_seg: int = 0
+    seconds_of_audio: float = 0.0
+    launches: int = 0
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+
+
+@dataclass
+class _Chunk:
+    c0: int
+    c1: int
+    s0: int          # first sample
+    s1: int
+    g0: int          # first segment
+    g1: int
+    e0: int          # first event
+    e1: int
+    clip_off: np.ndarray = field(default=None)
+    seg_off: np.ndarray = field(default=None)
+    evt_off: np.ndarray = field(default=None)
+    seg_time: np.ndarray = field(default=None)
+
+
+class FrontEnd:
+    def __init__(self, recipe: CqtRecipe = CqtRecipe(), device: Optional[int] = None, engine: Optional[int] = None,
+                 patch_mode: int = _lib.GTC_PATCH_VIT, img_size=(224, 224), chunk_segments: int = 16384,
+                 patch_batch: int = 4096):
+        self.recipe = recipe
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.dev = torch.device(f"cuda:{self.device}")
+        self.plan = ops.CqtPlan(recipe, device=self.device, engine=engine)
+        self.patch_mode = patch_mode
+        self.img_size = (int(img_size[0]), int(img_size[1]))
+        self.chunk_segments = int(chunk_segments)
+        self.patch_batch = int(patch_batch)
+        with torch.cuda.device(self.device):
+            self.s_copy, self.s_comp, self.s_out = (torch.cuda.Stream() for _ in range(3))
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ host-side planning (integer arithmetic only)
+    def plan_chunks(self, inp: ShardInputs) -> List[_Chunk]:
+        r = self.recipe
+        lens = np.asarray(inp.clip_lens, dtype=np.int64)
+        nseg = ops.segment_counts(lens, self.plan.seg_len, self.plan.seg_hop)
+        clip_off = np.concatenate([[0], np.cumsum(lens)])
+        seg_off = np.concatenate([[0], np.cumsum(nseg)])
+        chunks, c0 = [], 0
+        n_clips = len(lens)
+        while c0 < n_clips:
+            c1 = c0 + 1
+            while c1 < n_clips and seg_off[c1 + 1] - seg_off[c0] <= self.chunk_segments:
+                c1 += 1
+            ch = _Chunk(c0, c1, int(clip_off[c0]), int(clip_off[c1]), int(seg_off[c0]), int(seg_off[c1]),
+                        int(inp.evt_off[c0]), int(inp.evt_off[c1]))
+            assert ch.g1 - ch.g0 <= max(self.chunk_segments, int(nseg[c0]))
+            ch.clip_off = (clip_off[c0:c1 + 1] - clip_off[c0]).astype(np.int64)
+            ch.seg_off = (seg_off[c0:c1 + 1] - seg_off[c0]).astype(np.int64)
+            ch.evt_off = (np.asarray(inp.evt_off[c0:c1 + 1]) - inp.evt_off[c0]).astype(np.int64)
+            times = []
+            for c in range(c0, c1):
+                n = int(nseg[c])
+                if n:
+                    duration = float(lens[c]) / float(inp.sr)                 # librosa.get_duration(y, sr)
+                    times.append((np.arange(n, dtype=np.float64) + 0.5) * (duration / n))
+            ch.seg_time = np.concatenate(times) if times else np.zeros(0, dtype=np.float64)
+            chunks.append(ch)
+            c0 = c1
+        return chunks
+
+    def _buf(self, name, shape, dtype, pinned=False):
+        key = (name, pinned)
+        n = int(np.prod(shape))
+        t = self._bufs.get(key)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(n, dtype=dtype, pin_memory=True) if pinned else torch.empty(n, dtype=dtype, device=self.dev)
+            self._bufs[key] = t
+        return t[:n].view(shape)
+
+    # ------------------------------------------------------------------ execution
+    def run(self, inp: ShardInputs, device_inputs: bool = False, want_host_outputs: bool = True,
+            emit_patches: bool = True, consumer: Optional[Callable] = None, chunks: Optional[List[_Chunk]] = None) -> ShardOutputs:
+        """Process one shard.  ``consumer(patches, tabs_batch, first_segment_index)`` is called on the compute stream
+        for every patch batch (the training engine's input); without it patches are produced into a ring and dropped."""
+        plan, dev = self.plan, self.dev
+        chunks = self.plan_chunks(inp) if chunks is None else chunks
+        n_seg = chunks[-1].g1 if chunks else 0
+        out = ShardOutputs(n_seg=n_seg, seconds_of_audio=float(np.sum(inp.clip_lens)) / float(inp.sr))
+        nb, T = plan.n_bins, plan.n_frames
+        host_out = want_host_outputs and not device_inputs
+        if host_out:
+            out.db = self._buf("db_host", (n_seg, nb, T), torch.float32, pinned=True)
+            out.tabs = self._buf("tabs_host", (n_seg, 6, 19), torch.int8, pinned=True)
+        else:
+            out.db = self._buf("db_all", (n_seg, nb, T), torch.float32)
+            out.tabs = self._buf("tabs_all", (n_seg, 6, 19), torch.int8)
+        stats = self._buf("stats", (3,), torch.int64)
+        max_samples = max((c.s1 - c.s0 for c in chunks), default=1)
+        max_seg = max((c.g1 - c.g0 for c in chunks), default=1)
+        max_evt = max((c.e1 - c.e0 for c in chunks), default=1)
+        max_clips = max((c.c1 - c.c0 for c in chunks), default=1)
+        ws = plan.workspace(max_seg, max_clips)
+        pb = min(self.patch_batch, max(1, max_seg))
+        ev_done = [None, None]
+        # all chunk metadata (offsets, label times) goes up in one copy from pinned memory
+        meta_np = np.concatenate([np.concatenate([c.clip_off, c.seg_off, c.evt_off]) for c in chunks]).astype(np.int64) \
+            if chunks else np.zeros(1, np.int64)
+        time_np = np.concatenate([c.seg_time for c in chunks]) if chunks else np.zeros(1)
+        h_meta = self._buf("meta_host", (meta_np.size,), torch.int64, pinned=True)
+        h_time = self._buf("time_host", (max(1, time_np.size),), torch.float64, pinned=True)
+        h_meta.numpy()[:] = meta_np
+        h_time.numpy()[: time_np.size] = time_np
+        d_meta_all = self._buf("meta_dev", (meta_np.size,), torch.int64)
+        d_time_all = self._buf("time_dev", (max(1, time_np.size),), torch.float64)
+        with torch.cuda.device(self.device):
+            self.s_copy.wait_stream(torch.cuda.current_stream())
+            self.s_comp.wait_stream(torch.cuda.current_stream())
+            self.s_out.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.s_copy):
+                d_meta_all.copy_(h_meta, non_blocking=True)
+                d_time_all.copy_(h_time, non_blocking=True)
+                if not device_inputs:
+                    out.h2d_bytes += meta_np.nbytes + time_np.nbytes
+            with torch.cuda.stream(self.s_comp):
+                stats.zero_()
+            m_at = 0
+            for k, ch in enumerate(chunks):
+                b = k & 1
+                ns, ne, nc, ng = ch.s1 - ch.s0, ch.e1 - ch.e0, ch.c1 - ch.c0, ch.g1 - ch.g0
+                d_meta = d_meta_all[m_at: m_at + 3 * (nc + 1)]
+                m_at += 3 * (nc + 1)
+                d_time = d_time_all[ch.g0:ch.g1]
+                # ---- stage inputs
+                with torch.cuda.stream(self.s_copy):
+                    if ev_done[b] is not None:
+                        self.s_copy.wait_event(ev_done[b])            # buffers of chunk k-2 are free again
+                    if device_inputs:
+                        d_audio = inp.audio[ch.s0:ch.s1]
+                        d_ev = inp.events[:, ch.e0:ch.e1]
+                        d_on, d_du, d_pi = d_ev[0], d_ev[1], d_ev[2]
+                    else:
+                        d_audio = self._buf(f"audio{b}", (max_samples,), torch.float32)[:ns]
+                        d_audio.copy_(inp.audio[ch.s0:ch.s1], non_blocking=True)
+                        d_evb = self._buf(f"ev{b}", (3, max_evt), torch.float64)
+                        for j in range(3):                            # contiguous row slices -> plain async memcpys
+                            d_evb[j, :ne].copy_(inp.events[j, ch.e0:ch.e1], non_blocking=True)
+                        d_on, d_du, d_pi = d_evb[0, :ne], d_evb[1, :ne], d_evb[2, :ne]
+                        out.h2d_bytes += ns * 4 + ne * 24
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(self.s_copy)
+                d_clip_off, d_seg_off, d_evt_off = d_meta[: nc + 1], d_meta[nc + 1: 2 * nc + 2], d_meta[2 * nc + 2:]
+                # ---- kernels
+                with torch.cuda.stream(self.s_comp):
+                    self.s_comp.wait_event(ev_in)
+                    d_db = out.db[ch.g0:ch.g1] if not host_out else self._buf(f"db{b}", (max_seg, nb, T), torch.float32)[:ng]
+                    d_tabs = out.tabs[ch.g0:ch.g1] if not host_out else self._buf(f"tabs{b}", (max_seg, 6, 19), torch.int8)[:ng]
+                    if ng:
+                        plan.segments_db(d_audio, d_clip_off, d_seg_off, ng, out=d_db, workspace=ws)
+                        ops.rasterize_tabs(d_on, d_du, d_pi, d_evt_off, d_time, d_seg_off, out=d_tabs, stats=stats)
+                        out.launches += 4
+                        if emit_patches:
+                            for j, p0 in enumerate(range(0, ng, pb)):
+                                p1 = min(ng, p0 + pb)
+                                ring = self._buf(f"patch{j & 1}", (pb, 3) + self.img_size, torch.float32)[: p1 - p0]
+                                ops.patches(d_db[p0:p1], img_size=self.img_size, mode=self.patch_mode, out=ring)
+                                out.launches += 1
+                                if consumer is not None:
+                                    consumer(ring, d_tabs[p0:p1], ch.g0 + p0)
+                    ev_k = torch.cuda.Event()
+                    ev_k.record(self.s_comp)
+                # ---- results back to the host
+                if host_out:
+                    with torch.cuda.stream(self.s_out):
+                        self.s_out.wait_event(ev_k)
+                        out.db[ch.g0:ch.g1].copy_(d_db, non_blocking=True)
+                        out.tabs[ch.g0:ch.g1].copy_(d_tabs, non_blocking=True)
+                        out.d2h_bytes += ng * (nb * T * 4 + 114)
+                        ev_o = torch.cuda.Event()
+                        ev_o.record(self.s_out)
+                    ev_done[b] = ev_o
+                else:
+                    ev_done[b] = ev_k
+            # ---- stats (tiny) and join
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_stream(self.s_comp)
+                if host_out:
+                    h_stats = self._buf("stats_host", (3,), torch.int64, pinned=True)
+                    h_stats.copy_(stats, non_blocking=True)
+                    out.d2h_bytes += 24
+            torch.cuda.current_stream().wait_stream(self.s_out)
+            torch.cuda.current_stream().wait_stream(self.s_comp)
+            torch.cuda.current_stream().wait_stream(self.s_copy)
+        self._last_stats = (stats, self._bufs.get(("stats_host", True)) if host_out else None)
+        return out
+
+    def stats(self) -> np.ndarray:
+        """Synchronise and return (total, with_notes, with_first_string) of the last run."""
+        torch.cuda.synchronize(self.device)
+        dev_stats, host_stats = self._last_stats
+        return host_stats[:3].numpy().copy() if host_stats is not None else dev_stats.cpu().numpy()

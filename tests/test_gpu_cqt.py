@@ -124,7 +124,7 @@ def test_engines_agree(recipe, lib, clips):
     p0, p1 = ops.CqtPlan(recipe, engine=0), ops.CqtPlan(recipe, engine=1)
     a, b = run_gpu(p0, clips, True), run_gpu(p1, clips, True)
     scale = np.abs(b).max(axis=(1, 2), keepdims=True)
-    assert (np.abs(a - b) / scale).max() < 5e-6
+    assert (np.abs(a - b) / scale).max() < 2e-5      # fp32 FMA chain (K = 4410) vs 3xTF32 + split accumulation
     p0.close(); p1.close()
 
 
