@@ -180,7 +180,8 @@ static int run_segments(const gtc_plan* plan, const float* d_audio, const int64_
   const Workspace w = workspace_layout(p, n_seg, n_clips, complex_out);
   GTC_REQUIRE(workspace_bytes >= w.total, GTC_E_NOMEM, "gtc_cqt_segments: workspace of %zu bytes, %zu needed",
               workspace_bytes, w.total);
-  GTC_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 1023) == 0, GTC_E_ARG, "gtc_cqt_segments: workspace must be 1024-byte aligned");
+  // TMA needs 16-byte aligned global tiles; 256 is what cudaMalloc / torch's caching allocator (512) guarantee
+  GTC_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, GTC_E_ARG, "gtc_cqt_segments: workspace must be 256-byte aligned");
   int dev = -1;
   GTC_CUDA_CHECK(cudaGetDevice(&dev));
   GTC_REQUIRE(dev == p.device, GTC_E_ARG, "gtc_cqt_segments: plan belongs to device %d, current device is %d", p.device, dev);
