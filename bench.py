@@ -240,7 +240,8 @@ def run_cuda_arm(args):
     audio_host = torch.empty(audio_dev.shape, dtype=torch.float32, pin_memory=True)
     audio_host.copy_(audio_dev)
     lens = np.full(n_clips, n, dtype=np.int64)
-    fe = FrontEnd(recipe, device=local_rank, chunk_segments=args.chunk_segments, patch_batch=args.patch_batch)
+    fe = FrontEnd(recipe, device=local_rank, chunk_segments=args.chunk_segments, patch_batch=args.patch_batch,
+                  overlap=args.overlap, gemm_ctas=args.gemm_ctas, patch_ctas_per_sm=args.patch_ctas_per_sm)
     inp_dev = ShardInputs(audio_dev, lens, events_dev, evt_off, sr=SR)
     inp_host = ShardInputs(audio_host, lens, events_host, evt_off, sr=SR)
     chunks = fe.plan_chunks(inp_dev)
@@ -287,7 +288,10 @@ def run_cuda_arm(args):
     n_seg = out_dev.n_seg
     pb = min(args.patch_batch, n_seg)
     db_all = fe._bufs[("db_all", False)][: n_seg * 480].view(n_seg, 96, 5)
+    pb = min(pb, fe._bufs[("patch0", False)].numel() // (3 * 224 * 224))
     ring = fe._bufs[("patch0", False)][: pb * 3 * 224 * 224].view(pb, 3, 224, 224)
+    ops_set = __import__("gtc_b200.ops", fromlist=["set_option"])
+    ops_set.set_option(16, 0)                                   # time the patch kernel alone on the whole GPU
     from gtc_b200 import ops
     evs = []
     torch.cuda.synchronize()
@@ -349,6 +353,9 @@ def main():
     ap.add_argument("--chunk-segments", type=int, default=16384)
     ap.add_argument("--patch-batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap", action="store_true", help="run each chunk's patch kernel beside the next chunk's GEMM (slower on B200, see profiles/)")
+    ap.add_argument("--patch-ctas-per-sm", type=int, default=4, help="0 = do not limit the patch grid while overlapping")
+    ap.add_argument("--gemm-ctas", type=int, default=56, help="SMs given to the persistent tcgen05 GEMM while patches overlap")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

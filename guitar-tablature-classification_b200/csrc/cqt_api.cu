@@ -159,6 +159,15 @@ extern "C" int gtc_cqt_plan_destroy(gtc_plan* plan) {
   return GTC_OK;
 }
 
+extern "C" int gtc_cqt_plan_configure(gtc_plan* plan, int option, int value) {
+  GTC_REQUIRE(plan != nullptr && value >= 0, GTC_E_ARG, "gtc_cqt_plan_configure: bad argument");
+  switch (option) {
+    case GTC_OPT_TC_KSPLIT: plan->impl.tc_kb_per_split = value; return GTC_OK;
+    case GTC_OPT_GEMM_MAX_CTAS: plan->impl.tc_max_ctas = value; return GTC_OK;
+    default: set_error("gtc_cqt_plan_configure: unknown option %d", option); return GTC_E_ARG;
+  }
+}
+
 extern "C" int gtc_cqt_plan_parts(const gtc_plan* plan) { return plan ? plan->impl.parts : GTC_E_ARG; }
 
 extern "C" int gtc_cqt_workspace_bytes(const gtc_plan* plan, int64_t n_seg, int64_t n_clips, size_t* bytes) {
@@ -170,12 +179,13 @@ extern "C" int gtc_cqt_workspace_bytes(const gtc_plan* plan, int64_t n_seg, int6
 static int run_segments(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
                         int64_t n_clips, int64_t n_seg, float* d_out, bool complex_out, void* d_workspace,
                         size_t workspace_bytes, float power, float amin, float top_db, float cut_db, float floor_db,
-                        cudaStream_t st) {
+                        cudaStream_t st, int stages = 3 /* bit 0: framing, bit 1: contraction + finish */) {
   GTC_REQUIRE(plan != nullptr, GTC_E_ARG, "gtc_cqt_segments: plan is NULL");
   GTC_REQUIRE(n_clips >= 0 && n_seg >= 0, GTC_E_ARG, "gtc_cqt_segments: negative sizes");
   if (n_seg == 0) return GTC_OK;
   GTC_REQUIRE(n_clips > 0 && n_clips < (1 << 30), GTC_E_ARG, "gtc_cqt_segments: n_clips out of range");
-  GTC_REQUIRE(d_audio && d_clip_off && d_seg_off && d_out && d_workspace, GTC_E_ARG, "gtc_cqt_segments: null pointer");
+  GTC_REQUIRE(d_clip_off && d_seg_off && d_workspace && ((stages & 1) == 0 || d_audio) && ((stages & 2) == 0 || d_out),
+              GTC_E_ARG, "gtc_cqt_segments: null pointer");
   const PlanImpl& p = plan->impl;
   const Workspace w = workspace_layout(p, n_seg, n_clips, complex_out);
   GTC_REQUIRE(workspace_bytes >= w.total, GTC_E_NOMEM, "gtc_cqt_segments: workspace of %zu bytes, %zu needed",
@@ -190,8 +200,9 @@ static int run_segments(const gtc_plan* plan, const float* d_audio, const int64_
   float* xlo = reinterpret_cast<float*>(ws + w.off_xlo);
   float* gout = reinterpret_cast<float*>(ws + w.off_out);
   float* rowmax = reinterpret_cast<float*>(ws + w.off_rowmax);
-  int rc = launch_frame(p, d_audio, d_clip_off, d_seg_off, (int)n_clips, w.n_rows, w.n_rows_alloc, xhi, xlo, rowmax, st);
-  if (rc != GTC_OK) return rc;
+  int rc = GTC_OK;
+  if (stages & 1) rc = launch_frame(p, d_audio, d_clip_off, d_seg_off, (int)n_clips, w.n_rows, w.n_rows_alloc, xhi, xlo, rowmax, st);
+  if (rc != GTC_OK || (stages & 2) == 0) return rc;
   float* mag2 = complex_out ? nullptr : gout;
   float* cplx = complex_out ? gout : nullptr;
   if (p.engine == GTC_GEMM_TCGEN05_3XTF32)
@@ -210,6 +221,31 @@ extern "C" int gtc_cqt_segments_db(const gtc_plan* plan, const float* d_audio, c
   GTC_REQUIRE(power > 0.f && amin > 0.f, GTC_E_ARG, "gtc_cqt_segments_db: power and amin must be positive");
   return run_segments(plan, d_audio, d_clip_off, d_seg_off, n_clips, n_seg, d_out_db, false, d_workspace, workspace_bytes,
                       power, amin, top_db, cut_db, floor_db, (cudaStream_t)stream);
+}
+
+extern "C" int gtc_cqt_frame(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
+                             int64_t n_clips, int64_t n_seg, void* d_workspace, size_t workspace_bytes, gtc_stream_t stream) {
+  return run_segments(plan, d_audio, d_clip_off, d_seg_off, n_clips, n_seg, nullptr, false, d_workspace, workspace_bytes,
+                      4.f, 1e-5f, 80.f, -60.f, -120.f, (cudaStream_t)stream, 1);
+}
+
+extern "C" int gtc_cqt_contract_db(const gtc_plan* plan, const int64_t* d_clip_off, const int64_t* d_seg_off, int64_t n_clips,
+                                   int64_t n_seg, float* d_out_db, void* d_workspace, size_t workspace_bytes, float power,
+                                   float amin, float top_db, float cut_db, float floor_db, gtc_stream_t stream) {
+  GTC_REQUIRE(power > 0.f && amin > 0.f, GTC_E_ARG, "gtc_cqt_contract_db: power and amin must be positive");
+  return run_segments(plan, nullptr, d_clip_off, d_seg_off, n_clips, n_seg, d_out_db, false, d_workspace, workspace_bytes,
+                      power, amin, top_db, cut_db, floor_db, (cudaStream_t)stream, 2);
+}
+
+static int g_patch_max_ctas = 0;
+namespace gtc { int patch_max_ctas() { return g_patch_max_ctas; } }
+
+extern "C" int gtc_set_option(int option, int value) {
+  GTC_REQUIRE(value >= 0, GTC_E_ARG, "gtc_set_option: negative value");
+  switch (option) {
+    case GTC_OPT_PATCH_MAX_CTAS: g_patch_max_ctas = value; return GTC_OK;
+    default: set_error("gtc_set_option: unknown option %d", option); return GTC_E_ARG;
+  }
 }
 
 extern "C" int gtc_cqt_segments_complex(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off,

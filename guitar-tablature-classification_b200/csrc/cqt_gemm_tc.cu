@@ -385,7 +385,7 @@ int launch_gemm_tc(const PlanImpl& p, const float* d_xhi, const float* d_xlo, in
   if (rc != GTC_OK) return rc;
   TcParams prm;
   prm.nc = pick_nc(p.n_out);
-  prm.kb_per_split = p.tc_kb_per_split > 0 ? p.tc_kb_per_split : 12;
+  prm.kb_per_split = p.tc_kb_per_split > 0 ? p.tc_kb_per_split : 8;
   prm.n_chunks = (int)ceil_div(p.n_out, prm.nc);
   prm.n_out = p.n_out;
   prm.kb_per_part = p.kp / TBK;
@@ -393,7 +393,8 @@ int launch_gemm_tc(const PlanImpl& p, const float* d_xhi, const float* d_xlo, in
   prm.m_tiles = n_rows_pad / TBM;
   prm.mag2 = d_mag2; prm.cplx = d_cplx; prm.rowmax = d_rowmax;
   const int64_t n_tiles = prm.m_tiles * prm.n_chunks;
-  const unsigned grid = (unsigned)(n_tiles < p.sm_count ? n_tiles : p.sm_count);
+  const int64_t max_ctas = p.tc_max_ctas > 0 && p.tc_max_ctas < p.sm_count ? p.tc_max_ctas : p.sm_count;
+  const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
   const CUtensorMap& tm_ohi = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_hi);
   const CUtensorMap& tm_olo = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_lo);
   const bool cplx = d_cplx != nullptr;

@@ -31,6 +31,7 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 int sm_count_of_current_device();
+int patch_max_ctas();
 
 // index of the clip owning global item `g`:  largest c with off[c] <= g   (off has n+1 monotone entries)
 __device__ __forceinline__ int find_clip(const int64_t* __restrict__ off, int n, int64_t g) {
@@ -54,6 +55,7 @@ struct PlanImpl {
   int n_pad;        // n_out rounded up to 128
   int engine;
   int sm_count;
+  int tc_max_ctas;      // persistent GEMM grid limit (0 = sm_count)
   int tc_kb_per_split;  // K blocks per tensor-core accumulation split (0 = default), env GTC_TC_KSPLIT
   float* d_op;      // [n_pad][k_total]  operator, fp32, K padded per part (SIMT engine)
   float* d_op_hi;   // [n_pad][k_total]  tf32-representable high part (RN)

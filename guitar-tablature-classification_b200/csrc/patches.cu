@@ -3,12 +3,15 @@
 // align_corners=False, 3 identical channels) and the tensor contract of my_dataloader.py:17-21 (bilinear + ImageNet).
 //
 // This kernel is the binding roofline of the whole path: it reads 1 920 B and writes 602 112 B per segment, so it is a
-// pure HBM store stream.  Design: one CTA works on one segment at a time (grid = SMs x resident CTAs, grid-stride).
-//   1. the (n_bins x T) source is normalised into shared memory (next segment prefetched into registers meanwhile),
-//   2. vertical pass n_bins -> OH on the T-wide source (OH x T values, tiny),
-//   3. horizontal pass T -> OW fused with the store: every thread owns one float4 column group of the output row and
-//      keeps the 4 x T combined interpolation coefficients in registers, so a row costs 2 LDS.128 + 4T FFMA and three
-//      16-byte streaming stores (one per channel); a warp writes 512 contiguous bytes per store instruction.
+// pure HBM store stream.  Design:
+//   * work item = (segment, row block): OH is cut into `parts` row blocks so that even a training-size batch gives
+//     every SM several items and the tail of a launch is short; items are handed out by an atomic ticket, so CTAs that
+//     become resident late (e.g. when the CQT GEMM of the next chunk shares the GPU) simply take what is left;
+//   * per item the (n_bins x T) source is normalised into shared memory (the next item's source is prefetched into
+//     registers meanwhile), the vertical pass n_bins -> rows is done on the T-wide source (tiny), and the horizontal
+//     pass T -> OW is fused with the store: every thread owns one float4 column group and keeps its 4 x T combined
+//     interpolation coefficients in registers, so a row costs 2 LDS.128 + 4T FFMA and three 16-byte streaming
+//     stores (one per channel); a warp writes 512 contiguous bytes per store instruction.
 #include "gtc_common.cuh"
 
 namespace gtc {
@@ -19,6 +22,9 @@ struct PatchParams {
   int64_t n;
   int h_in, t_in, oh, ow;
   int mode;
+  int parts;            // row blocks per segment
+  int rows_per_part;
+  unsigned int* ticket; // zeroed before the launch
   float* out;
 };
 
@@ -55,22 +61,26 @@ __device__ __forceinline__ float normalise_db(float x) {           // ViT_datalo
 }
 
 constexpr int kPatchThreads = 224;
-constexpr int kMaxSrc = 4096;      // n_bins * T floats staged per segment
+constexpr int kMaxSrc = 4096;                          // n_bins * T floats staged per segment
+constexpr int kPreFast = (96 * 16) / kPatchThreads + 1;   // prefetch registers of the fast path
 
 // T_IN > 0: combined-coefficient fast path (OW % 4 == 0).  T_IN == 0: generic gather path, any size.
 template <int T_IN>
-__global__ void __launch_bounds__(kPatchThreads)
+__global__ void __launch_bounds__(kPatchThreads, T_IN == 5 ? 4 : 2)
 patch_kernel(const PatchParams p) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ unsigned int s_ticket;
   const int tid = threadIdx.x;
   const int t_in = T_IN > 0 ? T_IN : p.t_in;
   const int tp = (t_in + 3) & ~3;                     // padded row of the vertically interpolated image
   const int h_in = p.h_in, oh = p.oh, ow = p.ow;
   const int n_src = h_in * t_in;
+  const int rpp = p.rows_per_part;
+  const unsigned int n_items = (unsigned int)(p.n * p.parts);
 
   float* s_src = smem;                                // [h_in][t_in]
-  float* s_v = s_src + ((n_src + 3) & ~3);            // [oh][tp]
-  float* s_wy = s_v + oh * tp;                        // [oh][4]
+  float* s_v = s_src + ((n_src + 3) & ~3);            // [rows_per_part][tp]
+  float* s_wy = s_v + rpp * tp;                       // [oh][4]
   int* s_iy = reinterpret_cast<int*>(s_wy + oh * 4);  // [oh][4]
 
   for (int y = tid; y < oh; y += blockDim.x) {
@@ -79,6 +89,7 @@ patch_kernel(const PatchParams p) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { s_wy[y * 4 + i] = w[i]; s_iy[y * 4 + i] = idx[i]; }
   }
+  if (tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
 
   const bool flip = p.mode == GTC_PATCH_CNN;          // picture orientation: highest bin on the top row
   float ch_scale[3] = {1.f, 1.f, 1.f}, ch_bias[3] = {0.f, 0.f, 0.f};
@@ -88,10 +99,9 @@ patch_kernel(const PatchParams p) {
     for (int c = 0; c < 3; ++c) { ch_scale[c] = 1.f / stdv[c]; ch_bias[c] = -mean[c] / stdv[c]; }
   }
 
-  // per-thread horizontal coefficients
+  // per-thread horizontal coefficients: out[x] = sum_c coef[x][c] * v[c]
   constexpr int TC = T_IN > 0 ? T_IN : 1;
   float coef[4][TC];
-  int gidx[4][4]; float gw[4][4];                     // generic path
   const int quads = ow >> 2;
   int q = 0, r0 = 0, rstep = 1;
   if (T_IN > 0) {
@@ -109,27 +119,29 @@ patch_kernel(const PatchParams p) {
       }
     }
   }
-  (void)gidx; (void)gw;
 
-  constexpr int kPre = (kMaxSrc + kPatchThreads - 1) / kPatchThreads;   // prefetch registers (upper bound)
   const int n_pre = (n_src + blockDim.x - 1) / blockDim.x;
-  float pre[T_IN > 0 ? ((96 * 16) / kPatchThreads + 1) : 1];
-  constexpr int kPreFast = (96 * 16) / kPatchThreads + 1;
-  (void)kPre;
-
-  int64_t seg = blockIdx.x;
   const bool use_pre = T_IN > 0 && n_pre <= kPreFast;
-  if (use_pre && seg < p.n) {
-    const int64_t s = p.index ? p.index[seg] : seg;
+  float pre[kPreFast];
+  auto prefetch = [&](unsigned int item) {
+    const int64_t seg = item / p.parts;
+    const int64_t s = p.index ? __ldg(p.index + seg) : seg;
 #pragma unroll
     for (int k = 0; k < kPreFast; ++k) {
       const int o = tid + k * blockDim.x;
       pre[k] = (k < n_pre && o < n_src) ? __ldg(p.db + s * n_src + o) : 0.f;
     }
-  }
+  };
 
-  for (; seg < p.n; seg += gridDim.x) {
-    __syncthreads();                                   // previous segment's readers of s_src / s_v are done
+  __syncthreads();
+  unsigned int item = s_ticket;
+  if (use_pre && item < n_items) prefetch(item);
+
+  while (item < n_items) {
+    const int64_t seg = item / p.parts;
+    const int part = (int)(item - seg * p.parts);
+    const int y0 = part * rpp, y1 = min(oh, y0 + rpp);
+    __syncthreads();                                   // previous item's readers of s_src / s_v / s_ticket are done
     if (use_pre) {
 #pragma unroll
       for (int k = 0; k < kPreFast; ++k) {
@@ -146,35 +158,27 @@ patch_kernel(const PatchParams p) {
         s_src[(flip ? (h_in - 1 - r) : r) * t_in + c] = normalise_db(__ldg(p.db + s * n_src + o));
       }
     }
+    if (tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
     __syncthreads();
-    // vertical pass
-    for (int o = tid; o < oh * t_in; o += blockDim.x) {
-      const int y = o / t_in, c = o - y * t_in;
+    const unsigned int next = s_ticket;
+    // vertical pass for this row block
+    for (int o = tid; o < (y1 - y0) * t_in; o += blockDim.x) {
+      const int yy = o / t_in, c = o - yy * t_in;
+      const int y = y0 + yy;
       float a = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) a += s_wy[y * 4 + i] * s_src[s_iy[y * 4 + i] * t_in + c];
-      s_v[y * tp + c] = a;
+      s_v[yy * tp + c] = a;
     }
-    // prefetch the next segment's source while this one is being written out
-    if (use_pre) {
-      const int64_t nseg = seg + gridDim.x;
-      if (nseg < p.n) {
-        const int64_t s = p.index ? p.index[nseg] : nseg;
-#pragma unroll
-        for (int k = 0; k < kPreFast; ++k) {
-          const int o = tid + k * blockDim.x;
-          pre[k] = (k < n_pre && o < n_src) ? __ldg(p.db + s * n_src + o) : 0.f;
-        }
-      }
-    }
+    if (use_pre && next < n_items) prefetch(next);     // next item's source travels while this one is written out
     __syncthreads();
 
-    float* obase = p.out + seg * 3 * (int64_t)oh * ow;
     const int64_t plane = (int64_t)oh * ow;
+    float* obase = p.out + seg * 3 * plane;
     if (T_IN > 0) {
-      for (int y = r0; y < oh; y += rstep) {
-        float v[TC > 4 ? ((TC + 3) & ~3) : 8];
-        const float4* row = reinterpret_cast<const float4*>(s_v + y * tp);
+      for (int y = y0 + r0; y < y1; y += rstep) {
+        float v[(TC + 3) & ~3];
+        const float4* row = reinterpret_cast<const float4*>(s_v + (y - y0) * tp);
 #pragma unroll
         for (int k = 0; k < (TC + 3) / 4; ++k) {
           const float4 f = row[k];
@@ -200,19 +204,26 @@ patch_kernel(const PatchParams p) {
         }
       }
     } else {
-      for (int64_t o = tid; o < plane; o += blockDim.x) {
-        const int y = (int)(o / ow), x = (int)(o - (int64_t)y * ow);
+      const int n_out = (y1 - y0) * ow;
+      for (int o = tid; o < n_out; o += blockDim.x) {
+        const int yy = o / ow, x = o - yy * ow;
         int idx[4]; float w[4];
         axis_taps(x, t_in, ow, p.mode, idx, w);
         float a = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a += w[i] * s_v[y * tp + idx[i]];
+        for (int i = 0; i < 4; ++i) a += w[i] * s_v[yy * tp + idx[i]];
+        float* dst = obase + (int64_t)(y0 + yy) * ow + x;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) __stcs(obase + ch * plane + o, fmaf(a, ch_scale[ch], ch_bias[ch]));
+        for (int ch = 0; ch < 3; ++ch) __stcs(dst + ch * plane, fmaf(a, ch_scale[ch], ch_bias[ch]));
       }
     }
+    item = next;
   }
 }
+
+// tickets: a small ring of counters owned by the library; each launch zeroes and uses the next slot on its stream
+constexpr int kTicketSlots = 1024;
+__device__ unsigned int g_patch_tickets[kTicketSlots];
 
 }  // namespace gtc
 
@@ -227,25 +238,43 @@ extern "C" int gtc_patches(const float* d_db, const int64_t* d_index, int64_t n,
   GTC_REQUIRE(n_bins > 0 && n_frames > 0 && out_h > 0 && out_w > 0, GTC_E_ARG, "gtc_patches: non-positive size");
   GTC_REQUIRE((int64_t)n_bins * n_frames <= kMaxSrc, GTC_E_UNSUP, "gtc_patches: n_bins*n_frames > %d", kMaxSrc);
   GTC_REQUIRE(out_h <= 2048 && out_w <= 4096, GTC_E_UNSUP, "gtc_patches: output larger than 2048x4096");
-  PatchParams p{d_db, d_index, n, n_bins, n_frames, out_h, out_w, mode, d_out};
-  const int tp = (n_frames + 3) & ~3;
-  const size_t smem = sizeof(float) * (((size_t)n_bins * n_frames + 3) / 4 * 4 + (size_t)out_h * tp + (size_t)out_h * 8);
-  GTC_REQUIRE(smem <= 200 * 1024, GTC_E_UNSUP, "gtc_patches: %zu bytes of shared memory needed", smem);
+  GTC_REQUIRE(n < (int64_t)1 << 26, GTC_E_UNSUP, "gtc_patches: more than 2^26 items in one call");
   int sms = sm_count_of_current_device();
   if (sms <= 0) return GTC_E_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+
   const int quads = out_w / 4;
   const bool fast = (out_w % 4 == 0) && quads <= kPatchThreads && (n_frames == 5 || n_frames == 9) &&
                     n_bins * n_frames <= 96 * 16;
   int threads = kPatchThreads;
   if (fast) threads = (kPatchThreads / quads) * quads;
-  cudaStream_t st = (cudaStream_t)stream;
+  // row blocks: ~56 rows each (14 store iterations per thread), at least 1
+  int parts = out_h >= 112 ? (out_h + 55) / 56 : 1;
+  const int rpp = (out_h + parts - 1) / parts;
+  parts = (out_h + rpp - 1) / rpp;
+
+  static unsigned int* ticket_base[64] = {nullptr};   // per device: the symbol lives in every device's module image
+  static unsigned int next_slot = 0;
+  int dev = 0;
+  GTC_CUDA_CHECK(cudaGetDevice(&dev));
+  GTC_REQUIRE(dev >= 0 && dev < 64, GTC_E_UNSUP, "gtc_patches: device ordinal %d out of range", dev);
+  if (!ticket_base[dev]) GTC_CUDA_CHECK(cudaGetSymbolAddress((void**)&ticket_base[dev], g_patch_tickets));
+  unsigned int* ticket = ticket_base[dev] + (__atomic_fetch_add(&next_slot, 1u, __ATOMIC_RELAXED) % kTicketSlots);
+  GTC_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
+
+  PatchParams p{d_db, d_index, n, n_bins, n_frames, out_h, out_w, mode, parts, rpp, ticket, d_out};
+  const int tp = (n_frames + 3) & ~3;
+  const size_t smem = sizeof(float) * (((size_t)n_bins * n_frames + 3) / 4 * 4 + (size_t)rpp * tp + (size_t)out_h * 8);
+  GTC_REQUIRE(smem <= 200 * 1024, GTC_E_UNSUP, "gtc_patches: %zu bytes of shared memory needed", smem);
   auto launch = [&](auto kern) -> int {
     if (smem > 48 * 1024) GTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     GTC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)sms * per_sm;
-    if (grid > n) grid = n;
+    const int64_t items = n * parts;
+    if (grid > items) grid = items;
+    if (patch_max_ctas() > 0 && grid > patch_max_ctas()) grid = patch_max_ctas();
     kern<<<(unsigned)grid, threads, smem, st>>>(p);
     GTC_CUDA_CHECK(cudaGetLastError());
     return GTC_OK;

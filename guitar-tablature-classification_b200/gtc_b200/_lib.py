@@ -13,6 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libgtc.so")
 
 GTC_GEMM_TCGEN05_3XTF32 = 0
 GTC_GEMM_SIMT_FP32 = 1
+GTC_OPT_TC_KSPLIT = 1
+GTC_OPT_GEMM_MAX_CTAS = 2
+GTC_OPT_PATCH_MAX_CTAS = 16
 GTC_PATCH_VIT = 0
 GTC_PATCH_CNN = 1
 
@@ -25,8 +28,12 @@ PROTOTYPES = {
     "gtc_cqt_plan_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _i]),
     "gtc_cqt_plan_destroy": (_i, [_vp]),
     "gtc_cqt_plan_parts": (_i, [_vp]),
+    "gtc_cqt_plan_configure": (_i, [_vp, _i, _i]),
     "gtc_cqt_workspace_bytes": (_i, [_vp, _i64, _i64, C.POINTER(_sz)]),
     "gtc_cqt_segments_db": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp]),
+    "gtc_cqt_frame": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz, _vp]),
+    "gtc_cqt_contract_db": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp]),
+    "gtc_set_option": (_i, [_i, _i]),
     "gtc_cqt_segments_complex": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "gtc_rasterize_tabs": (_i, [_vp] * 11 + [_i64, _i64, _vp, _vp, _vp]),
     "gtc_labels_argmax": (_i, [_vp, _vp, _i64, _vp, _vp]),

@@ -60,7 +60,12 @@ class CqtPlan:
                                                self.n_frames, op.ctypes.data_as(C.c_void_p), self.engine),
                        "gtc_cqt_plan_create")
         self._h = handle
+        self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
         self._ws: Optional[torch.Tensor] = None
+
+    def configure(self, option: int, value: int) -> None:
+        """Tuning knobs (GTC_OPT_TC_KSPLIT, GTC_OPT_GEMM_MAX_CTAS)."""
+        _lib.check(_lib.load().gtc_cqt_plan_configure(self._h, int(option), int(value)), "gtc_cqt_plan_configure")
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -104,6 +109,21 @@ class CqtPlan:
                                                    r.floor_db, _stream()), "gtc_cqt_segments_db")
         return out
 
+    def frame(self, audio: torch.Tensor, clip_off: torch.Tensor, seg_off: torch.Tensor, n_seg: int, workspace: torch.Tensor) -> None:
+        """Stage 1 of segments_db: audio -> tf32 hi/lo row matrix in the workspace."""
+        _need_cuda(audio, clip_off, seg_off, workspace)
+        _lib.check(_lib.load().gtc_cqt_frame(self._h, _ptr(audio), _ptr(clip_off), _ptr(seg_off), clip_off.numel() - 1, n_seg,
+                                             _ptr(workspace), workspace.numel(), _stream()), "gtc_cqt_frame")
+
+    def contract_db(self, clip_off: torch.Tensor, seg_off: torch.Tensor, n_seg: int, out: torch.Tensor, workspace: torch.Tensor) -> torch.Tensor:
+        """Stage 2 of segments_db: tensor-core contraction + dB finish from a framed workspace."""
+        _need_cuda(clip_off, seg_off, out, workspace)
+        r = self.recipe
+        _lib.check(_lib.load().gtc_cqt_contract_db(self._h, _ptr(clip_off), _ptr(seg_off), clip_off.numel() - 1, n_seg, _ptr(out),
+                                                   _ptr(workspace), workspace.numel(), r.power, r.amin, r.top_db, r.cut_db,
+                                                   r.floor_db, _stream()), "gtc_cqt_contract_db")
+        return out
+
     def segments_complex(self, audio: torch.Tensor, clip_off: torch.Tensor, seg_off: torch.Tensor, n_seg: int) -> torch.Tensor:
         """[n_seg, n_bins, T] complex64 (== librosa.cqt of every segment)."""
         _need_cuda(audio, clip_off, seg_off)
@@ -113,6 +133,11 @@ class CqtPlan:
         _lib.check(_lib.load().gtc_cqt_segments_complex(self._h, _ptr(audio), _ptr(clip_off), _ptr(seg_off), n_clips, n_seg,
                                                         _ptr(out), _ptr(ws), ws.numel(), _stream()), "gtc_cqt_segments_complex")
         return torch.view_as_complex(out)
+
+
+def set_option(option: int, value: int) -> None:
+    """Process-wide tunables of libgtc (GTC_OPT_PATCH_MAX_CTAS)."""
+    _lib.check(_lib.load().gtc_set_option(int(option), int(value)), "gtc_set_option")
 
 
 def rasterize_tabs(onset, dur, pitch, evt_off, seg_time, seg_off, contour=None, stats: Optional[torch.Tensor] = None,

@@ -62,7 +62,11 @@ class _Chunk:
 class FrontEnd:
     def __init__(self, recipe: CqtRecipe = CqtRecipe(), device: Optional[int] = None, engine: Optional[int] = None,
                  patch_mode: int = _lib.GTC_PATCH_VIT, img_size=(224, 224), chunk_segments: int = 16384,
-                 patch_batch: int = 4096):
+                 patch_batch: int = 4096, overlap: bool = False, gemm_ctas: int = 64,
+                 patch_ctas_per_sm: int = 4):
+        """``overlap=True`` runs each chunk's patch kernel beside the next chunk's GEMM on disjoint SMs.  Measured on
+        B200 (profiles/r01_overlap_sweep.md) it is SLOWER than running them back to back: the patch kernel needs all
+        148 SMs to saturate HBM stores, so the default keeps the two kernels sequential."""
         self.recipe = recipe
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.dev = torch.device(f"cuda:{self.device}")
@@ -71,8 +75,17 @@ class FrontEnd:
         self.img_size = (int(img_size[0]), int(img_size[1]))
         self.chunk_segments = int(chunk_segments)
         self.patch_batch = int(patch_batch)
+        self.overlap = bool(overlap)
+        self.gemm_ctas = int(gemm_ctas) if self.overlap else 0
+        if self.gemm_ctas > 0:
+            self.plan.configure(_lib.GTC_OPT_GEMM_MAX_CTAS, self.gemm_ctas)
+            if patch_ctas_per_sm > 0:
+                # the patch CTAs must not back-fill the SMs the persistent GEMM runs on (see run())
+                ops.set_option(_lib.GTC_OPT_PATCH_MAX_CTAS, (self.plan.sm_count - self.gemm_ctas) * int(patch_ctas_per_sm))
         with torch.cuda.device(self.device):
-            self.s_copy, self.s_comp, self.s_out = (torch.cuda.Stream() for _ in range(3))
+            self.s_copy, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            self.s_comp = torch.cuda.Stream(priority=-1)              # GEMM path: scheduled ahead of pending patch CTAs
+            self.s_patch = torch.cuda.Stream(priority=0)
         self._bufs = {}
 
     # ------------------------------------------------------------------ host-side planning (integer arithmetic only)
@@ -139,6 +152,7 @@ class FrontEnd:
         ws = plan.workspace(max_seg, max_clips)
         pb = min(self.patch_batch, max(1, max_seg))
         ev_done = [None, None]
+        ev_free = [[], []]
         # all chunk metadata (offsets, label times) goes up in one copy from pinned memory
         meta_np = np.concatenate([np.concatenate([c.clip_off, c.seg_off, c.evt_off]) for c in chunks]).astype(np.int64) \
             if chunks else np.zeros(1, np.int64)
@@ -153,6 +167,7 @@ class FrontEnd:
             self.s_copy.wait_stream(torch.cuda.current_stream())
             self.s_comp.wait_stream(torch.cuda.current_stream())
             self.s_out.wait_stream(torch.cuda.current_stream())
+            self.s_patch.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.s_copy):
                 d_meta_all.copy_(h_meta, non_blocking=True)
                 d_time_all.copy_(h_time, non_blocking=True)
@@ -160,6 +175,23 @@ class FrontEnd:
                     out.h2d_bytes += meta_np.nbytes + time_np.nbytes
             with torch.cuda.stream(self.s_comp):
                 stats.zero_()
+            def emit(job, gate, s_p):
+                jb, jch, j_db, j_tabs, _ = job
+                jng = jch.g1 - jch.g0
+                with torch.cuda.stream(s_p):
+                    s_p.wait_event(gate)
+                    for j, p0 in enumerate(range(0, jng, pb)):
+                        p1 = min(jng, p0 + pb)
+                        ring = self._buf(f"patch{j & 1}", (pb, 3) + self.img_size, torch.float32)[: p1 - p0]
+                        ops.patches(j_db[p0:p1], img_size=self.img_size, mode=self.patch_mode, out=ring)
+                        out.launches += 1
+                        if consumer is not None:
+                            consumer(ring, j_tabs[p0:p1], jch.g0 + p0)
+                    ev_p = torch.cuda.Event()
+                    ev_p.record(s_p)
+                ev_free[jb].append(ev_p)
+
+            pending = None
             m_at = 0
             for k, ch in enumerate(chunks):
                 b = k & 1
@@ -186,25 +218,35 @@ class FrontEnd:
                     ev_in = torch.cuda.Event()
                     ev_in.record(self.s_copy)
                 d_clip_off, d_seg_off, d_evt_off = d_meta[: nc + 1], d_meta[nc + 1: 2 * nc + 2], d_meta[2 * nc + 2:]
-                # ---- kernels
+                # ---- CQT (frame + tcgen05 GEMM + dB finish) and labels
                 with torch.cuda.stream(self.s_comp):
                     self.s_comp.wait_event(ev_in)
+                    for e in ev_free[b]:
+                        self.s_comp.wait_event(e)                     # chunk k-2's patches / D2H released db{b}, tabs{b}
                     d_db = out.db[ch.g0:ch.g1] if not host_out else self._buf(f"db{b}", (max_seg, nb, T), torch.float32)[:ng]
                     d_tabs = out.tabs[ch.g0:ch.g1] if not host_out else self._buf(f"tabs{b}", (max_seg, 6, 19), torch.int8)[:ng]
+                    ev_g = None
                     if ng:
-                        plan.segments_db(d_audio, d_clip_off, d_seg_off, ng, out=d_db, workspace=ws)
+                        plan.frame(d_audio, d_clip_off, d_seg_off, ng, ws)
+                        if self.overlap:
+                            ev_g = torch.cuda.Event()                 # "the GEMM of chunk k is the next thing on s_comp"
+                            ev_g.record(self.s_comp)
+                        plan.contract_db(d_clip_off, d_seg_off, ng, d_db, ws)
                         ops.rasterize_tabs(d_on, d_du, d_pi, d_evt_off, d_time, d_seg_off, out=d_tabs, stats=stats)
                         out.launches += 4
-                        if emit_patches:
-                            for j, p0 in enumerate(range(0, ng, pb)):
-                                p1 = min(ng, p0 + pb)
-                                ring = self._buf(f"patch{j & 1}", (pb, 3) + self.img_size, torch.float32)[: p1 - p0]
-                                ops.patches(d_db[p0:p1], img_size=self.img_size, mode=self.patch_mode, out=ring)
-                                out.launches += 1
-                                if consumer is not None:
-                                    consumer(ring, d_tabs[p0:p1], ch.g0 + p0)
                     ev_k = torch.cuda.Event()
                     ev_k.record(self.s_comp)
+                ev_done[b] = ev_k                                     # audio{b} / ev{b} may be overwritten after this
+                ev_free[b] = []
+                # ---- patches.  Overlap mode: the store-bound patch kernel of chunk k-1 is released on its own
+                #      (low-priority) stream at the moment the tensor-core GEMM of chunk k becomes runnable on the
+                #      high-priority stream: the GEMM takes its `gemm_ctas` SMs first, the patch CTAs fill the rest.
+                if emit_patches and self.overlap:
+                    if pending is not None:
+                        emit(pending, ev_g if ev_g is not None else ev_k, self.s_patch)
+                    pending = (b, ch, d_db, d_tabs, ev_k) if ng else None
+                elif emit_patches and ng:
+                    emit((b, ch, d_db, d_tabs, ev_k), ev_k, self.s_comp)
                 # ---- results back to the host
                 if host_out:
                     with torch.cuda.stream(self.s_out):
@@ -214,9 +256,9 @@ class FrontEnd:
                         out.d2h_bytes += ng * (nb * T * 4 + 114)
                         ev_o = torch.cuda.Event()
                         ev_o.record(self.s_out)
-                    ev_done[b] = ev_o
-                else:
-                    ev_done[b] = ev_k
+                    ev_free[b].append(ev_o)
+            if pending is not None:                                   # last chunk's patches: nothing left to overlap with
+                emit(pending, pending[4], self.s_patch)
             # ---- stats (tiny) and join
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_stream(self.s_comp)
@@ -227,6 +269,7 @@ class FrontEnd:
             torch.cuda.current_stream().wait_stream(self.s_out)
             torch.cuda.current_stream().wait_stream(self.s_comp)
             torch.cuda.current_stream().wait_stream(self.s_copy)
+            torch.cuda.current_stream().wait_stream(self.s_patch)
         self._last_stats = (stats, self._bufs.get(("stats_host", True)) if host_out else None)
         return out
 

@@ -61,6 +61,10 @@ int         gtc_device_info(int device, int* sm_count, int* cc_major, int* cc_mi
 int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int seg_hop, int n_bins, int n_frames,
                         const float* h_operator, int gemm_engine);
 int gtc_cqt_plan_destroy(gtc_plan* plan);
+/* tuning knobs; call before the plan is shared between threads.  Returns GTC_E_ARG for unknown options. */
+#define GTC_OPT_TC_KSPLIT      1   /* k-blocks (32 fp32 each) accumulated inside the tensor core before an fp32 add; default 8 */
+#define GTC_OPT_GEMM_MAX_CTAS  2   /* limit of the persistent GEMM grid (0 = one CTA per SM); lets other kernels share the GPU */
+int gtc_cqt_plan_configure(gtc_plan* plan, int option, int value);
 /* number of operator rows sharing one audio row (P = seg_len/seg_hop when it divides, else 1) */
 int gtc_cqt_plan_parts(const gtc_plan* plan);
 /* bytes of scratch gtc_cqt_segments_db needs for `n_seg` segments spread over `n_clips` clips */
@@ -79,6 +83,18 @@ int gtc_cqt_segments_db(const gtc_plan* plan, const float* d_audio, const int64_
                         void* d_workspace, size_t workspace_bytes,
                         float power, float amin, float top_db, float cut_db, float floor_db,
                         gtc_stream_t stream);
+/* The two stages of gtc_cqt_segments_db as separate calls (same workspace, same stream order), so that a caller can
+ * put an event between the framing kernel and the tensor-core contraction: the pipeline uses it to start the previous
+ * chunk's patch kernel exactly when the next GEMM becomes runnable, so the two share the GPU. */
+int gtc_cqt_frame(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
+                  int64_t n_clips, int64_t n_seg, void* d_workspace, size_t workspace_bytes, gtc_stream_t stream);
+int gtc_cqt_contract_db(const gtc_plan* plan, const int64_t* d_clip_off, const int64_t* d_seg_off, int64_t n_clips,
+                        int64_t n_seg, float* d_out_db, void* d_workspace, size_t workspace_bytes,
+                        float power, float amin, float top_db, float cut_db, float floor_db, gtc_stream_t stream);
+/* process-wide tunables */
+#define GTC_OPT_PATCH_MAX_CTAS 16  /* grid limit of the patch kernel (0 = SMs x resident CTAs) */
+int gtc_set_option(int option, int value);
+
 /* Same contraction, complex output before |.|: d_out_c [n_seg, n_bins, n_frames, 2] fp32 (== librosa.cqt). */
 int gtc_cqt_segments_complex(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off,
                              const int64_t* d_seg_off, int64_t n_clips, int64_t n_seg, float* d_out_c,
