@@ -1,0 +1,232 @@
+"""Drop-in for the reference's ``jam_to_tablature.py``: ``GuitarTablatureExtractor`` with the same constructor and
+methods, label arithmetic evaluated by libgtc's bit-exact rasteriser on a B200.
+
+Reference semantics that are kept (file:line = /root/reference/jam_to_tablature.py):
+  * pooled ``note_midi`` notes active at ``time <= t < time + duration`` (:119-141), lowest-fret string rule with
+    Python round-half-even (:91-107), (6, 19) int8 multi-hot, unplayed strings all-zero;
+  * pitch-contour fallback when no note is active (:145-178, :317-318), exceptions swallowed -> zeros (:319-320);
+  * label grid from the number of CQT pictures on disk: ``t_i = (i + 0.5) * duration / num_images`` (:259-274);
+  * one file per segment ``{out}/{base}/{base}_{i:04d}.npy`` (:323-324); stats dict total / with_notes /
+    with_first_string (:283-287, :327-331, :376-378); errors are printed, never raised (:262-264, :297-300, :307-309).
+Changed on purpose: all segments of all files go through ONE kernel launch in ``process_all_files``; the wav is not
+decoded to find its duration (header only); ``jams`` is optional (a built-in JSON reader is used when it is absent);
+pictures may be ``.png`` (reference) or the ``.npy`` feature files this repo's new_cqt.py/cqt.py write.
+"""
+from __future__ import annotations
+
+import os
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from gtc_b200 import audio_io, events, ops
+
+
+def _load_jam(path):
+    try:
+        import jams  # type: ignore
+        return jams.load(os.path.abspath(str(path)))
+    except ImportError:
+        return events.load_jams(path)
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _t(a, dtype):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(_dev())
+
+
+def _rasterize(note_sets, contour_sets, times_per_clip):
+    """note_sets[c] = (onset, dur, pitch); contour_sets[c] = (time, midi, conf, kind) or None; -> (labels, stats)."""
+    (on, du, pi), eoff = events.pack_clips(note_sets)
+    soff = np.concatenate([[0], np.cumsum([len(t) for t in times_per_clip])]).astype(np.int64)
+    times = np.concatenate(times_per_clip) if len(times_per_clip) else np.zeros(0)
+    contour = None
+    if any(c is not None for c in contour_sets):
+        empty = (np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0, np.int8))
+        (ct, cm, cc, ck), coff = events.pack_clips([c if c is not None else empty for c in contour_sets])
+        contour = (_t(ct, np.float64), _t(cm, np.float64), _t(cc, np.float64), _t(ck, np.int8), _t(coff, np.int64))
+    tabs, stats = ops.rasterize_tabs(_t(on, np.float64), _t(du, np.float64), _t(pi, np.float64), _t(eoff, np.int64),
+                                     _t(times, np.float64), _t(soff, np.int64), contour=contour)
+    return tabs.cpu().numpy(), stats.cpu().numpy(), soff
+
+
+class GuitarTablatureExtractor:
+    def __init__(self, jams_dir, audio_dir, cqt_images_dir, output_dir):
+        self.jams_dir = Path(jams_dir)
+        self.audio_dir = Path(audio_dir)
+        self.cqt_images_dir = Path(cqt_images_dir)
+        self.output_dir = Path(output_dir)
+        self.output_dir.mkdir(exist_ok=True, parents=True)
+        self.num_strings = 6
+        self.num_frets = 19
+        self.open_string_pitches = [40, 45, 50, 55, 59, 64]
+        for label, p in (("JAMS", self.jams_dir), ("Audio", self.audio_dir), ("CQT images", self.cqt_images_dir)):
+            print(f"{label} directory: {p} (exists: {p.exists()})")
+        print(f"Output directory: {self.output_dir}")
+
+    # ------------------------------------------------------------------ small helpers with the reference's names
+    def check_file_exists(self, file_path):
+        path = Path(file_path)
+        return path.exists() and path.is_file()
+
+    def midi_to_tablature(self, midi_pitches, confidence=None):
+        """List of MIDI pitches (numbers or {'pitch'|'value': ..} dicts) -> (6, 19) int8 (reference :55-109)."""
+        keep = []
+        for i, pitch in enumerate(midi_pitches):
+            conf = confidence[i] if confidence is not None else 1.0
+            if conf < 0.5:                                   # raises TypeError on None exactly like the reference
+                continue
+            p = events._resolve_pitch(pitch)
+            if p is not None:
+                keep.append(p)
+        if not keep:
+            return np.zeros((self.num_strings, self.num_frets), dtype=np.int8)
+        n = len(keep)
+        tabs, _, _ = _rasterize([(np.zeros(n), np.ones(n), np.asarray(keep, dtype=np.float64))], [None], [np.array([0.5])])
+        return tabs[0]
+
+    def extract_tablature_from_jams(self, jam, segment_time):
+        tabs, _, _ = _rasterize([events.marshal_notes(jam)], [None], [np.array([float(segment_time)])])
+        return tabs[0]
+
+    def extract_tablature_from_pitch_contour(self, jam, segment_time):
+        ct, cm, cc, ck = events.marshal_contours(jam)
+        if np.any((np.abs(ct - float(segment_time)) < 0.05) & (ck == 1)):
+            raise TypeError("'<' not supported between instances of 'NoneType' and 'float'")   # reference :70
+        empty = (np.zeros(0), np.zeros(0), np.zeros(0))
+        tabs, _, _ = _rasterize([empty], [(ct, cm, cc, ck)], [np.array([float(segment_time)])])
+        return tabs[0]
+
+    def get_cqt_segment_times(self, audio_file, segment_duration=0.2):
+        if not self.check_file_exists(audio_file):
+            print(f"Audio file does not exist or is not accessible: {audio_file}")
+            return []
+        try:
+            duration = audio_io.wav_duration(audio_file)
+        except Exception as e:
+            print(f"Failed to load audio file {audio_file}: {str(e)}")
+            return []
+        return [i * segment_duration for i in range(int(duration / segment_duration))]   # starts, as the code does (:208-209)
+
+    def find_cqt_image(self, base_name, segment_idx):
+        stems = [f"{base_name}_{segment_idx:04d}", f"{base_name}-{segment_idx:04d}", f"{base_name}_{segment_idx:03d}",
+                 f"{base_name}-{segment_idx:03d}", f"{base_name}_{segment_idx}", f"{base_name}-{segment_idx}"]
+        for ext in (".png", ".npy"):
+            for stem in stems:
+                path = self.cqt_images_dir / (stem + ext)
+                if path.exists():
+                    return path
+        return None
+
+    # ------------------------------------------------------------------ per-file work split into host prep + one launch
+    def _prepare(self, jams_file, audio_file):
+        base_name = os.path.splitext(os.path.basename(audio_file))[0]
+        pictures = sorted(self.cqt_images_dir.glob(f"{base_name}_*.png")) or sorted(self.cqt_images_dir.glob(f"{base_name}_*.npy"))
+        num_images = len(pictures)
+        if num_images == 0:
+            print(f"No CQT images found for {base_name}")
+            return None
+        duration = audio_io.wav_duration(audio_file)
+        times = events.segment_times(duration, num_images)
+        keep = [i for i in range(num_images) if self.find_cqt_image(base_name, i) is not None]
+        for i in sorted(set(range(num_images)) - set(keep)):
+            print(f"Warning: CQT image not found for segment {i} of {base_name}")
+        notes = (np.zeros(0), np.zeros(0), np.zeros(0))
+        contour, loaded = None, False
+        try:
+            jam = _load_jam(jams_file)
+            notes, contour, loaded = events.marshal_notes(jam), events.marshal_contours(jam), True
+        except Exception as e:
+            print(f"Failed to load JAMS file {jams_file}: {str(e)}")
+            print("Proceeding with empty tablature data")
+        return {"base": base_name, "keep": np.asarray(keep, dtype=np.int64), "times": times[keep] if keep else np.zeros(0),
+                "notes": notes, "contour": contour, "loaded": loaded}
+
+    def _run(self, jobs):
+        jobs = [j for j in jobs if j is not None]
+        results = {}
+        if not jobs:
+            return results
+        tabs, _, soff = _rasterize([j["notes"] for j in jobs], [j["contour"] for j in jobs], [j["times"] for j in jobs])
+        for c, j in enumerate(jobs):
+            out_dir = self.output_dir / j["base"]
+            out_dir.mkdir(exist_ok=True)
+            mine = tabs[soff[c]:soff[c + 1]]
+            stats = {'total': 0, 'with_notes': 0, 'with_first_string': 0}
+            for i, tab in zip(j["keep"], mine):
+                audio_io.save_label(out_dir / f"{j['base']}_{int(i):04d}.npy", tab)
+                stats['total'] += 1
+                stats['with_notes'] += int(tab.sum() > 0)
+                stats['with_first_string'] += int(tab[0].sum() > 0)
+            results[j["base"]] = stats
+        return results
+
+    def process_file(self, jams_file, audio_file, segment_duration=0.2):
+        print(f"Processing file: {os.path.splitext(os.path.basename(audio_file))[0]}")
+        job = self._prepare(jams_file, audio_file)
+        if job is None:
+            return {'total': 0, 'with_notes': 0, 'with_first_string': 0}
+        return self._run([job])[job["base"]]
+
+    def process_all_files(self, segment_duration=0.2):
+        jams_files = list(self.jams_dir.glob("*.jams"))
+        if not jams_files:
+            print(f"No JAMS files found in {self.jams_dir}")
+            return
+        print(f"Found {len(jams_files)} JAMS files")
+        jobs = []
+        for jams_file in jams_files:
+            base_name = os.path.splitext(jams_file.name)[0]
+            audio_file = None
+            for prefix in ['hex_debleeded_', 'hex_debleeded-', 'hex_debleeded', '']:
+                candidate = self.audio_dir / f"{prefix}{base_name}.wav"
+                if candidate.exists():
+                    audio_file = candidate
+                    break
+            if not audio_file:
+                print(f"Audio file not found for {base_name}")
+                continue
+            try:
+                jobs.append(self._prepare(jams_file, audio_file))
+            except Exception as e:
+                print(f"Error preparing {base_name}: {str(e)}")
+        all_stats = {'total': 0, 'with_notes': 0, 'with_first_string': 0}
+        for stats in self._run(jobs).values():
+            for key in all_stats:
+                all_stats[key] += stats[key]
+        print("Processing complete. Statistics:")
+        print(f"Total tablature files: {all_stats['total']}")
+        print(f"Files with any notes: {all_stats['with_notes']}")
+        print(f"Files with any notes on first string: {all_stats['with_first_string']}")
+        return all_stats
+
+    def validate_tablature_data(self):
+        tablature_files = list(self.output_dir.rglob("*.npy"))
+        if not tablature_files:
+            print("No tablature files found!")
+            return
+        sample_count = min(100, len(tablature_files))
+        picks = np.random.choice(len(tablature_files), sample_count, replace=False)
+        counts, first = [], 0
+        for k in picks:
+            tab = np.load(tablature_files[int(k)])
+            counts.append(int(tab.sum()))
+            first += int(tab[0].sum() > 0)
+        stats = {'empty': sum(c == 0 for c in counts), 'with_notes': sum(c > 0 for c in counts),
+                 'with_first_string': first, 'avg_notes_per_tab': float(np.mean(counts))}
+        print(f"Found {len(tablature_files)} tablature files; sampled {sample_count}: {stats}")
+        return stats
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser(description="JAMS annotations -> per-segment (6,19) tablature .npy files")
+    ap.add_argument("jams_dir"); ap.add_argument("audio_dir"); ap.add_argument("cqt_images_dir"); ap.add_argument("output_dir")
+    a = ap.parse_args()
+    ex = GuitarTablatureExtractor(a.jams_dir, a.audio_dir, a.cqt_images_dir, a.output_dir)
+    ex.process_all_files(segment_duration=0.2)
+    ex.validate_tablature_data()

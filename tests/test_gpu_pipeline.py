@@ -67,3 +67,37 @@ def test_frontend_matches_direct_ops(lib, shard_inputs, recipe):
     for g0, p, t in seen[:4]:
         assert np.abs(p[0].cpu().numpy() - po.vit_patch(db_e2e[g0])).max() < 3e-5
         assert np.array_equal(t[0].cpu().numpy(), want[g0])
+
+
+def test_sharded_run_equals_single_run(lib, shard_inputs, recipe):
+    """SURVEY.md section 4: shard the clip list N ways, concatenate, compare bit-for-bit with the 1-way result;
+    the gathered stats equal the serial sums (ranks emulated one after the other on the one GPU of the test box)."""
+    from gtc_b200 import ops, shard
+    from gtc_b200.pipeline import FrontEnd, ShardInputs
+    audio, lens, ev, eoff = shard_inputs
+    dev = torch.device("cuda")
+    fe = FrontEnd(recipe, chunk_segments=64, patch_batch=32)
+    clip_off = np.concatenate([[0], np.cumsum(lens)])
+
+    def run(clip_ids):
+        a = np.concatenate([audio[clip_off[c]:clip_off[c + 1]] for c in clip_ids])
+        e = np.concatenate([ev[:, eoff[c]:eoff[c + 1]] for c in clip_ids], axis=1)
+        eo = np.concatenate([[0], np.cumsum([eoff[c + 1] - eoff[c] for c in clip_ids])]).astype(np.int64)
+        inp = ShardInputs(torch.from_numpy(a).to(dev), lens[clip_ids], torch.from_numpy(np.ascontiguousarray(e)).to(dev), eo, sr=SR)
+        out = fe.run(inp, device_inputs=True, emit_patches=False)
+        torch.cuda.synchronize()
+        return out.db.cpu().numpy().copy(), out.tabs.cpu().numpy().copy(), fe.stats().copy()
+
+    full_db, full_tabs, full_stats = run(np.arange(len(lens)))
+    counts = ops.segment_counts(lens, 4410, 2205)
+    for world in (2, 3):
+        owners = [shard.partition_round_robin(len(lens), r, world) for r in range(world)]
+        res = [run(o) for o in owners]
+        assert np.array_equal(shard.merge_sharded([r[0] for r in res], owners, counts), full_db)
+        assert np.array_equal(shard.merge_sharded([r[1] for r in res], owners, counts), full_tabs)
+        gathered = torch.stack([shard.ShardStats(n_clips=len(o), n_segments=int(counts[o].sum()), total=int(r[2][0]),
+                                                 with_notes=int(r[2][1]), with_first_string=int(r[2][2])).as_tensor()
+                                for o, r in zip(owners, res)])
+        tot = shard.reduce_stats(gathered)
+        assert [tot["total"], tot["with_notes"], tot["with_first_string"]] == list(full_stats)
+        assert tot["n_clips"] == len(lens) and tot["n_segments"] == int(counts.sum())

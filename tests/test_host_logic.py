@@ -1,0 +1,131 @@
+"""CPU tests of the host-side logic: WAV/.npy I/O, JAMS marshalling, splits, sharding (no CUDA calls)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gtc_b200 import audio_io, events, loaders, ops, shard
+from oracle import labels_oracle as lo
+
+
+def test_wav_roundtrip_matches_librosa_semantics(tmp_path):
+    rng = np.random.default_rng(0)
+    y = rng.uniform(-0.9, 0.9, (1000, 2))
+    q = np.clip(np.round(y * 32768), -32768, 32767).astype(np.int16)
+    import scipy.io.wavfile
+    scipy.io.wavfile.write(tmp_path / "a.wav", 22050, q)
+    got, sr = audio_io.load_wav(tmp_path / "a.wav")
+    assert sr == 22050 and got.dtype == np.float32 and got.shape == (1000,)
+    want = (q.astype(np.float32) / 32768).mean(axis=1)               # soundfile scaling + librosa.to_mono
+    assert np.abs(got - want).max() < 1e-7
+    seg, _ = audio_io.load_wav(tmp_path / "a.wav", offset=0.01, duration=0.02)
+    assert np.array_equal(seg, got[int(0.01 * 22050): int(0.01 * 22050) + int(0.02 * 22050)])
+    assert audio_io.wav_duration(tmp_path / "a.wav") == 1000 / 22050
+
+
+def test_npy_layouts(tmp_path):
+    f = np.arange(96 * 5, dtype=np.float32).reshape(96, 5)
+    audio_io.save_feature(tmp_path / "f.npy", f)
+    raw = open(tmp_path / "f.npy", "rb").read()
+    assert b"'fortran_order': True" in raw[:128] and b"'<f4'" in raw[:128] and len(raw) == 128 + 1920
+    assert np.array_equal(np.load(tmp_path / "f.npy"), f)
+    tab = np.zeros((6, 19), np.int8)
+    tab[2, 3] = 1
+    audio_io.save_label(tmp_path / "t.npy", tab)
+    raw = open(tmp_path / "t.npy", "rb").read()
+    assert len(raw) == 242 and b"'|i1'" in raw[:128] and b"'fortran_order': False" in raw[:128] and b"(6, 19)" in raw[:128]
+
+
+def test_label_fixture_format_matches_reference_files():
+    """tests/golden/labels_*.npy are verbatim copies of three reference label files (format pin only)."""
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    names = sorted(f for f in os.listdir(gold) if f.startswith("ref_label_"))
+    assert len(names) >= 3
+    for n in names:
+        raw = open(os.path.join(gold, n), "rb").read()
+        a = np.load(os.path.join(gold, n))
+        assert a.shape == (6, 19) and a.dtype == np.int8 and set(np.unique(a)) <= {0, 1} and len(raw) == 242
+
+
+def test_jams_json_reader_and_marshalling(tmp_path):
+    doc = {"file_metadata": {"duration": 3.0},
+           "annotations": [{"namespace": "note_midi", "data": [{"time": 0.5, "duration": 1.0, "value": 45.2, "confidence": None},
+                                                                {"time": 1.0, "duration": 0.5, "value": {"pitch": 50}, "confidence": 1},
+                                                                {"time": 1.0, "duration": 0.5, "value": {"other": 1}, "confidence": 1},
+                                                                {"time": 1.0, "duration": 0.5, "value": "abc", "confidence": 1}]},
+                           {"namespace": "pitch_contour", "data": {"time": [0.0, 0.01, 0.02], "duration": [0, 0, 0],
+                                                                   "value": [{"frequency": 110.0, "voiced": True}, {"frequency": 0.0}, 220.0],
+                                                                   "confidence": [0.9, 0.9, None]}}]}
+    p = tmp_path / "x.jams"
+    p.write_text(json.dumps(doc))
+    jam = events.load_jams(p)
+    on, du, pi = events.marshal_notes(jam)
+    assert list(on) == [0.5, 1.0] and list(pi) == [45.2, 50.0]
+    ct, cm, cc, ck = events.marshal_contours(jam)
+    assert list(ct) == [0.0, 0.02] and list(ck) == [0, 1] and abs(cm[0] - 45.0) < 1e-12
+    # the same objects drive the oracle (attribute-compatible with jams.JAMS)
+    assert lo.extract_tablature_from_jams(jam, 0.6).sum() == 1
+
+
+def test_random_split_reproduces_torch(tmp_path):
+    class Fake:
+        def __len__(self):
+            return 103
+    sizes = loaders.split_sizes(103, 0.8, 0.1)
+    assert sizes == (82, 10, 11)
+    mine = loaders.random_split(Fake(), list(sizes), generator=torch.Generator().manual_seed(42))
+    ref = torch.utils.data.random_split(range(103), list(sizes), generator=torch.Generator().manual_seed(42))
+    for a, b in zip(mine, ref):
+        assert a.indices == list(b.indices)
+
+
+def test_segment_counts():
+    assert list(ops.segment_counts([661500, 4410, 4409, 0, 6615], 4410, 2205)) == [299, 1, 0, 0, 2]
+
+
+def test_partitions_cover_every_clip_once():
+    for world in (1, 2, 3, 8):
+        parts = [shard.partition_round_robin(10, r, world) for r in range(world)]
+        assert sorted(np.concatenate(parts).tolist()) == list(range(10))
+        durs = [30.0, 14.6, 22.0, 29.5, 15.0, 16.0, 30.0, 21.0, 18.5, 25.0]
+        parts = [shard.partition_balanced(durs, r, world) for r in range(world)]
+        assert sorted(np.concatenate(parts).tolist()) == list(range(10))
+        loads = [sum(durs[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= 30.0
+
+
+def test_merge_sharded_restores_clip_order():
+    counts = np.array([3, 0, 2, 4, 1])
+    full = np.arange(10 * 2).reshape(10, 2)
+    off = np.concatenate([[0], np.cumsum(counts)])
+    owners = [shard.partition_round_robin(5, r, 2) for r in range(2)]
+    outs = [np.concatenate([full[off[c]:off[c + 1]] for c in own]) for own in owners]
+    assert np.array_equal(shard.merge_sharded(outs, owners, counts), full)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    own = shard.partition_round_robin(7, rank, world)
+    st = shard.ShardStats(n_clips=len(own), n_segments=int(own.sum()) + 1, n_samples=100 * (rank + 1), total=10 * (rank + 1),
+                          with_notes=rank + 2, with_first_string=rank, n_skipped=0, elapsed_ns=1000 * (rank + 1))
+    g = shard.gather_stats(st.as_tensor())
+    q.put((rank, g.tolist(), shard.reduce_stats(g)))
+    dist.destroy_process_group()
+
+
+def test_stats_gather_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert res[0][1] == res[1][1]                                  # every rank sees the same [2, 8] table
+    tot = res[0][2]
+    assert tot["n_clips"] == 7 and tot["total"] == 30 and tot["with_notes"] == 5 and tot["elapsed_ns"] == 2000
