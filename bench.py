@@ -240,7 +240,7 @@ def run_cuda_arm(args):
     audio_host = torch.empty(audio_dev.shape, dtype=torch.float32, pin_memory=True)
     audio_host.copy_(audio_dev)
     lens = np.full(n_clips, n, dtype=np.int64)
-    fe = FrontEnd(recipe, device=local_rank, chunk_segments=args.chunk_segments, patch_batch=args.patch_batch,
+    fe = FrontEnd(recipe, device=local_rank, engine=args.engine, chunk_segments=args.chunk_segments, patch_batch=args.patch_batch,
                   overlap=args.overlap, gemm_ctas=args.gemm_ctas, patch_ctas_per_sm=args.patch_ctas_per_sm)
     inp_dev = ShardInputs(audio_dev, lens, events_dev, evt_off, sr=SR)
     inp_host = ShardInputs(audio_host, lens, events_host, evt_off, sr=SR)
@@ -353,6 +353,7 @@ def main():
     ap.add_argument("--chunk-segments", type=int, default=16384)
     ap.add_argument("--patch-batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", type=int, default=None, help="GEMM engine: 0 tcgen05 3xTF32, 1 SIMT fp32, 2 tcgen05 fp16x2 (default: library default)")
     ap.add_argument("--overlap", action="store_true", help="run each chunk's patch kernel beside the next chunk's GEMM (slower on B200, see profiles/)")
     ap.add_argument("--patch-ctas-per-sm", type=int, default=4, help="0 = do not limit the patch grid while overlapping")
     ap.add_argument("--gemm-ctas", type=int, default=56, help="SMs given to the persistent tcgen05 GEMM while patches overlap")

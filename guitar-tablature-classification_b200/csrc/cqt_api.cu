@@ -4,6 +4,7 @@
 #include <math.h>
 #include <new>
 #include <vector>
+#include <cuda_fp16.h>
 #include "gtc_common.cuh"
 
 namespace gtc {
@@ -45,7 +46,7 @@ static Workspace workspace_layout(const PlanImpl& p, int64_t n_seg, int64_t n_cl
   w.n_rows = n_seg + n_clips * (p.parts - 1);
   w.n_rows_pad = round_up(w.n_rows > 0 ? w.n_rows : 1, 128);
   w.n_rows_alloc = w.n_rows_pad + 8;                    // rows read with the +p offset of the last tile
-  const size_t xbytes = (size_t)w.n_rows_alloc * p.kp * sizeof(float);
+  const size_t xbytes = (size_t)w.n_rows_alloc * p.kp * (size_t)p.elem_bytes;
   const size_t obytes = (size_t)w.n_rows_pad * (complex_out ? p.n_out : p.n_out / 2) * sizeof(float);
   size_t o = 0;
   auto take = [&](size_t b) { size_t at = o; o += (b + 1023) & ~(size_t)1023; return at; };
@@ -84,7 +85,7 @@ extern "C" int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int 
   *out = nullptr;
   GTC_REQUIRE(h_operator != nullptr, GTC_E_ARG, "gtc_cqt_plan_create: h_operator is NULL (design it with gtc_b200.cqt_design)");
   GTC_REQUIRE(seg_len > 0 && seg_hop > 0 && n_bins > 0 && n_frames > 0, GTC_E_ARG, "gtc_cqt_plan_create: non-positive size");
-  GTC_REQUIRE(gemm_engine == GTC_GEMM_TCGEN05_3XTF32 || gemm_engine == GTC_GEMM_SIMT_FP32, GTC_E_ARG,
+  GTC_REQUIRE(gemm_engine == GTC_GEMM_TCGEN05_3XTF32 || gemm_engine == GTC_GEMM_SIMT_FP32 || gemm_engine == GTC_GEMM_TCGEN05_FP16X2, GTC_E_ARG,
               "gtc_cqt_plan_create: unknown engine %d", gemm_engine);
   GTC_CUDA_CHECK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -101,46 +102,72 @@ extern "C" int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int 
   const bool divides = (seg_len % seg_hop == 0) && (seg_len / seg_hop <= 8);
   p.parts = divides ? seg_len / seg_hop : 1;
   p.row_len = divides ? seg_hop : seg_len;
-  p.kp = (int)round_up(p.row_len, 32);
+  const bool half = gemm_engine == GTC_GEMM_TCGEN05_FP16X2;
+  const bool tensor = gemm_engine != GTC_GEMM_SIMT_FP32;
+  p.elem_bytes = half ? 2 : 4;
+  p.kb_elems = 128 / p.elem_bytes;
+  p.x_scale = half ? 256.f : 1.f;                       // |x| < 256 stays finite in fp16; lo part normal down to |x| ~ 1e-3
+  p.out_scale = 1.f;
+  p.kp = (int)round_up(p.row_len, p.kb_elems);
   p.k_total = p.parts * p.kp;
   p.n_out = 2 * n_bins * n_frames;
   p.n_pad = (int)round_up(p.n_out, 128);
   p.engine = gemm_engine;
   p.sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("GTC_TC_KSPLIT")) p.tc_kb_per_split = atoi(e);
-  if (gemm_engine == GTC_GEMM_TCGEN05_3XTF32 && (p.n_out % 16 != 0)) {
+  if (tensor && (p.n_out % 16 != 0)) {
     delete plan;
     set_error("gtc_cqt_plan_create: tcgen05 engine needs 2*n_bins*n_frames %% 16 == 0 (got %d)", p.n_out);
     return GTC_E_UNSUP;
   }
 
   const size_t elems = (size_t)p.n_pad * p.k_total;
-  std::vector<float> raw(elems, 0.f), hi(elems, 0.f), lo(elems, 0.f);
-  for (int n = 0; n < p.n_out; ++n) {
-    const float* src = h_operator + (size_t)n * seg_len;
-    float* r = raw.data() + (size_t)n * p.k_total;
-    float* h = hi.data() + (size_t)n * p.k_total;
-    float* l = lo.data() + (size_t)n * p.k_total;
-    for (int j = 0; j < seg_len; ++j) {
-      const int part = j / p.row_len, k = j - part * p.row_len;
-      const size_t at = (size_t)part * p.kp + k;
-      const float v = src[j];
-      r[at] = v;
-      h[at] = tf32_rn_host(v);
-      l[at] = v - h[at];
-    }
-  }
   int rc = GTC_OK;
-  auto up = [&](float** d, const std::vector<float>& h) -> int {
-    GTC_CUDA_CHECK(cudaMalloc((void**)d, elems * sizeof(float)));
-    GTC_CUDA_CHECK(cudaMemcpy(*d, h.data(), elems * sizeof(float), cudaMemcpyHostToDevice));
+  auto up = [&](void** d, const void* h, size_t bytes) -> int {
+    GTC_CUDA_CHECK(cudaMalloc(d, bytes));
+    GTC_CUDA_CHECK(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
     return GTC_OK;
   };
-  if ((rc = up(&p.d_op, raw)) != GTC_OK || (rc = up(&p.d_op_hi, hi)) != GTC_OK || (rc = up(&p.d_op_lo, lo)) != GTC_OK) {
-    gtc_cqt_plan_destroy(plan);
-    return rc;
+  auto at_of = [&](int j) { const int part = j / p.row_len; return (size_t)part * p.kp + (j - part * p.row_len); };
+  if (half) {
+    // fp16x2: A * 2^s = hi + lo with s such that max|A| * 2^s <= 2^13; absolute quantisation error <= 2^-25 (fp16
+    // subnormal spacing / 2) against row maxima of ~2^13, i.e. < 2^-36 relative -- see DESIGN.md 3.1
+    float amax = 0.f;
+    for (size_t i = 0; i < (size_t)p.n_out * seg_len; ++i) amax = fmaxf(amax, fabsf(h_operator[i]));
+    int s = amax > 0.f ? 13 - (int)ceilf(log2f(amax)) : 0;
+    if (s > 24) s = 24;
+    if (s < -24) s = -24;
+    const float a_scale = ldexpf(1.f, s);
+    p.out_scale = 1.f / (a_scale * p.x_scale);
+    std::vector<__half> hi(elems, __float2half(0.f)), lo(elems, __float2half(0.f));
+    for (int n = 0; n < p.n_out; ++n)
+      for (int j = 0; j < seg_len; ++j) {
+        const float v = h_operator[(size_t)n * seg_len + j] * a_scale;
+        const size_t at = (size_t)n * p.k_total + at_of(j);
+        hi[at] = __float2half_rn(v);
+        lo[at] = __float2half_rn(v - __half2float(hi[at]));
+      }
+    if ((rc = up(&p.d_op_hi, hi.data(), elems * 2)) != GTC_OK || (rc = up(&p.d_op_lo, lo.data(), elems * 2)) != GTC_OK) {
+      gtc_cqt_plan_destroy(plan);
+      return rc;
+    }
+  } else {
+    std::vector<float> raw(elems, 0.f), hi(elems, 0.f), lo(elems, 0.f);
+    for (int n = 0; n < p.n_out; ++n)
+      for (int j = 0; j < seg_len; ++j) {
+        const float v = h_operator[(size_t)n * seg_len + j];
+        const size_t at = (size_t)n * p.k_total + at_of(j);
+        raw[at] = v;
+        hi[at] = tf32_rn_host(v);
+        lo[at] = v - hi[at];
+      }
+    if ((!tensor && (rc = up((void**)&p.d_op, raw.data(), elems * 4)) != GTC_OK) ||
+        (tensor && ((rc = up(&p.d_op_hi, hi.data(), elems * 4)) != GTC_OK || (rc = up(&p.d_op_lo, lo.data(), elems * 4)) != GTC_OK))) {
+      gtc_cqt_plan_destroy(plan);
+      return rc;
+    }
   }
-  if (gemm_engine == GTC_GEMM_TCGEN05_3XTF32 && (rc = tc_plan_init(p)) != GTC_OK) {
+  if (tensor && (rc = tc_plan_init(p)) != GTC_OK) {
     gtc_cqt_plan_destroy(plan);
     return rc;
   }
@@ -196,8 +223,8 @@ static int run_segments(const gtc_plan* plan, const float* d_audio, const int64_
   GTC_CUDA_CHECK(cudaGetDevice(&dev));
   GTC_REQUIRE(dev == p.device, GTC_E_ARG, "gtc_cqt_segments: plan belongs to device %d, current device is %d", p.device, dev);
   char* ws = static_cast<char*>(d_workspace);
-  float* xhi = reinterpret_cast<float*>(ws + w.off_xhi);
-  float* xlo = reinterpret_cast<float*>(ws + w.off_xlo);
+  void* xhi = ws + w.off_xhi;
+  void* xlo = ws + w.off_xlo;
   float* gout = reinterpret_cast<float*>(ws + w.off_out);
   float* rowmax = reinterpret_cast<float*>(ws + w.off_rowmax);
   int rc = GTC_OK;
@@ -205,10 +232,10 @@ static int run_segments(const gtc_plan* plan, const float* d_audio, const int64_
   if (rc != GTC_OK || (stages & 2) == 0) return rc;
   float* mag2 = complex_out ? nullptr : gout;
   float* cplx = complex_out ? gout : nullptr;
-  if (p.engine == GTC_GEMM_TCGEN05_3XTF32)
+  if (p.engine != GTC_GEMM_SIMT_FP32)
     rc = launch_gemm_tc(p, xhi, xlo, w.n_rows_pad, w.n_rows_alloc, mag2, cplx, rowmax, st);
   else
-    rc = launch_gemm_simt(p, xhi, xlo, w.n_rows_pad, mag2, cplx, rowmax, st);
+    rc = launch_gemm_simt(p, (const float*)xhi, (const float*)xlo, w.n_rows_pad, mag2, cplx, rowmax, st);
   if (rc != GTC_OK) return rc;
   if (complex_out) return launch_finish_complex(p, cplx, d_seg_off, (int)n_clips, n_seg, d_out, st);
   return launch_finish_db(p, mag2, rowmax, d_seg_off, (int)n_clips, n_seg, d_out, power, amin, top_db, cut_db, floor_db, st);

@@ -9,6 +9,7 @@
 //
 // Finish: per segment, mag2 = |C|^2 of all n_bins*T outputs plus the row maximum -> |C|^power ->
 // librosa.amplitude_to_db(ref=np.amax, amin, top_db) -> cqt_lim (cqt.py:56-58), written as [n_seg, n_bins, T].
+#include <cuda_fp16.h>
 #include "gtc_common.cuh"
 
 namespace gtc {
@@ -19,10 +20,31 @@ __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float(u);
 }
 
+// fp16x2 operands: the (power-of-two scaled) sample is split into hi = fp16(x) and lo = fp16(x - hi): 22 mantissa bits
+__device__ __forceinline__ void split_store(__half* hi, __half* lo, int64_t i, const float (&v)[4], float scale) {
+  __half h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float x = v[j] * scale;
+    h[j] = __float2half_rn(x);
+    l[j] = __float2half_rn(x - __half2float(h[j]));
+  }
+  reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+  reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+}
+__device__ __forceinline__ void split_store(float* hi, float* lo, int64_t i, const float (&v)[4], float) {
+  float4 h, l;
+  h.x = tf32_rn(v[0]); h.y = tf32_rn(v[1]); h.z = tf32_rn(v[2]); h.w = tf32_rn(v[3]);
+  l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
+  reinterpret_cast<float4*>(hi)[i] = h;
+  reinterpret_cast<float4*>(lo)[i] = l;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256)
 frame_kernel(const float* __restrict__ audio, const int64_t* __restrict__ clip_off, const int64_t* __restrict__ seg_off,
              int n_clips, int parts, int row_len, int seg_hop, int kp, int64_t n_rows, int64_t n_rows_alloc,
-             float* __restrict__ xhi, float* __restrict__ xlo, float* __restrict__ rowmax, int64_t n_rowmax) {
+             T* __restrict__ xhi, T* __restrict__ xlo, float scale, float* __restrict__ rowmax, int64_t n_rowmax) {
   const int vec_per_row = kp >> 2;
   const int64_t total = n_rows_alloc * vec_per_row;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -43,25 +65,27 @@ frame_kernel(const float* __restrict__ audio, const int64_t* __restrict__ clip_o
       for (int j = 0; j < 4; ++j)
         if (k0 + j < row_len && base + j < clip_end) v[j] = __ldg(audio + base + j);
     }
-    float4 h, l;
-    h.x = tf32_rn(v[0]); h.y = tf32_rn(v[1]); h.z = tf32_rn(v[2]); h.w = tf32_rn(v[3]);
-    l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
-    reinterpret_cast<float4*>(xhi)[i] = h;
-    reinterpret_cast<float4*>(xlo)[i] = l;
+    split_store(xhi, xlo, i, v, scale);
     if (k0 == 0 && row < n_rowmax) rowmax[row] = 0.f;
   }
 }
 
 int launch_frame(const PlanImpl& p, const float* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
-                 int n_clips, int64_t n_rows, int64_t n_rows_alloc, float* d_xhi, float* d_xlo, float* d_rowmax,
+                 int n_clips, int64_t n_rows, int64_t n_rows_alloc, void* d_xhi, void* d_xlo, float* d_rowmax,
                  cudaStream_t st) {
   const int64_t total = n_rows_alloc * (p.kp / 4);
   int64_t blocks = ceil_div(total, 256);
   const int64_t cap = (int64_t)p.sm_count * 16;
   if (blocks > cap) blocks = cap;
   const int64_t n_rowmax = round_up(n_rows, 128);
-  frame_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_audio, d_clip_off, d_seg_off, n_clips, p.parts, p.row_len, p.seg_hop,
-                                                  p.kp, n_rows, n_rows_alloc, d_xhi, d_xlo, d_rowmax, n_rowmax);
+  if (p.elem_bytes == 2)
+    frame_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(d_audio, d_clip_off, d_seg_off, n_clips, p.parts, p.row_len,
+                                                          p.seg_hop, p.kp, n_rows, n_rows_alloc, (__half*)d_xhi, (__half*)d_xlo,
+                                                          p.x_scale, d_rowmax, n_rowmax);
+  else
+    frame_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(d_audio, d_clip_off, d_seg_off, n_clips, p.parts, p.row_len,
+                                                         p.seg_hop, p.kp, n_rows, n_rows_alloc, (float*)d_xhi, (float*)d_xlo,
+                                                         1.f, d_rowmax, n_rowmax);
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;
 }

@@ -31,6 +31,7 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 struct TcParams {
   int nc;                // operator rows per tile
+  float out_scale;       // 2^-(x_scale + operator scale) of the fp16x2 engine, 1 otherwise
   int kb_per_split;      // k-blocks accumulated inside the tensor core before an fp32 RN add in registers
   int n_chunks;          // tiles along N
   int n_out;             // valid operator rows
@@ -87,6 +88,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -109,9 +118,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B                         [61,64)
   return d;
 }
-// cute::UMMA::InstrDescriptor : c=F32, a=b=TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// cute::UMMA::InstrDescriptor : c=F32, a=b=fmt (0 = F16, 2 = TF32), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(uint32_t fmt, int m, int n) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // tcgen05.ld of 8 columns (32x32b.x8)
@@ -126,12 +135,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&r)[8]) {
 // the ~1650 accumulator updates of a full K pass biases the result by ~3e-5 relative -- measured on B200 -- so K is
 // cut into splits of `kb_per_split` k-blocks, each accumulated from zero in one of two TMEM stages and then summed
 // in fp32 (round-to-nearest) by the epilogue warps while the next split is already being multiplied.
-template <int NC, bool kComplex>
+// kHalf: operands are fp16 hi/lo pairs (kind::f16, 64 elements per 128-byte k-block, 16 per MMA) instead of tf32 pairs
+// (kind::tf32, 32 per k-block, 8 per MMA); in bytes the tiles, the swizzle and the +32 B k-step are identical.
+template <int NC, bool kComplex, bool kHalf>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo,
                const TcParams prm) {
   constexpr int H = NC / 2;                  // columns per epilogue warp
+  constexpr int EPK = kHalf ? 64 : 32;       // operand elements per k-block
   static_assert(NC % 16 == 0 && NC <= TMAXN && H % 8 == 0, "unsupported tile width");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bars[2 * TSTAGES + 4];
@@ -184,11 +196,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           mbar_wait(bar_empty(stage), phase ^ 1);
           mbar_expect_tx(bar_full(stage), stage_tx);
           const int p = kb / prm.kb_per_part;
-          const int kx = (kb - p * prm.kb_per_part) * TBK;
+          const int kx = (kb - p * prm.kb_per_part) * EPK;
           tma_load_2d(st_xhi(stage), &tm_xhi, bar_full(stage), kx, row0 + p);
           tma_load_2d(st_xlo(stage), &tm_xlo, bar_full(stage), kx, row0 + p);
-          tma_load_2d(st_ohi(stage), &tm_ohi, bar_full(stage), kb * TBK, n0);
-          tma_load_2d(st_olo(stage), &tm_olo, bar_full(stage), kb * TBK, n0);
+          tma_load_2d(st_ohi(stage), &tm_ohi, bar_full(stage), kb * EPK, n0);
+          tma_load_2d(st_olo(stage), &tm_olo, bar_full(stage), kb * EPK, n0);
           if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -197,7 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(TBM, NC);
+      const uint32_t idesc = make_idesc(kHalf ? 0u : 2u, TBM, NC);
       int stage = 0; uint32_t phase = 0;
       uint32_t it = 0;                                       // accumulator-stage use counter (one per K split)
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -216,9 +228,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 #pragma unroll
             for (int k = 0; k < TBK / TUMMA_K; ++k) {
               const uint64_t adv = (uint64_t)((k * TUMMA_K * 4) >> 4);   // +32 B per k-step inside the swizzle row
-              umma_tf32(tmem_d, dxh + adv, doh + adv, idesc, (first && k == 0) ? 0u : 1u);
-              umma_tf32(tmem_d, dxl + adv, doh + adv, idesc, 1u);
-              umma_tf32(tmem_d, dxh + adv, dol + adv, idesc, 1u);
+              if (kHalf) {
+                umma_f16(tmem_d, dxh + adv, doh + adv, idesc, (first && k == 0) ? 0u : 1u);
+                umma_f16(tmem_d, dxl + adv, doh + adv, idesc, 1u);
+                umma_f16(tmem_d, dxh + adv, dol + adv, idesc, 1u);
+              } else {
+                umma_tf32(tmem_d, dxh + adv, doh + adv, idesc, (first && k == 0) ? 0u : 1u);
+                umma_tf32(tmem_d, dxl + adv, doh + adv, idesc, 1u);
+                umma_tf32(tmem_d, dxh + adv, dol + adv, idesc, 1u);
+              }
             }
             umma_commit(bar_empty(stage));                  // frees the smem slot when these MMAs retire
             if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
@@ -265,7 +283,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty(acc));
       }
-      // tile finished: |.|^2 + row max, or the raw complex values
+      // tile finished: undo the power-of-two operand scaling (exact), then |.|^2 + row max, or the raw complex values
+      if (kHalf) {
+#pragma unroll
+        for (int c = 0; c < H; ++c) sum[c] *= prm.out_scale;
+      }
       if (kComplex) {
 #pragma unroll
         for (int c = 0; c < H; c += 4)
@@ -316,14 +338,15 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2D fp32 row-major [rows][cols] tensor, box = 32 floats x box_rows, 128-byte swizzle, OOB -> zeros
-static int encode_2d(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+static int encode_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int elem_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return GTC_E_CUDA;
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {cols * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)TBK, box_rows};
+  cuuint64_t gstr[1] = {cols * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_rows};          // 128-byte swizzle row
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+  CUresult r = fn(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GTC_REQUIRE(r == CUDA_SUCCESS, GTC_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -340,8 +363,10 @@ static int pick_nc(int n_out) {
 
 template <int NC>
 static int set_smem_attr() {
-  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<NC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<NC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<NC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<NC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
   return GTC_OK;
 }
 
@@ -350,9 +375,9 @@ int tc_plan_init(PlanImpl& p) {
   p.tmap_op_hi = &maps[0];
   p.tmap_op_lo = &maps[1];
   const int nc = pick_nc(p.n_out);
-  int rc = encode_2d(&maps[0], p.d_op_hi, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)nc);
+  int rc = encode_2d(&maps[0], p.d_op_hi, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)nc, p.elem_bytes);
   if (rc != GTC_OK) return rc;
-  rc = encode_2d(&maps[1], p.d_op_lo, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)nc);
+  rc = encode_2d(&maps[1], p.d_op_lo, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)nc, p.elem_bytes);
   if (rc != GTC_OK) return rc;
   switch (nc) {
     case 256: return set_smem_attr<256>();
@@ -369,26 +394,32 @@ void tc_plan_free(PlanImpl& p) {
 }
 
 template <int NC>
-static void launch_nc(bool cplx, unsigned grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b,
+static void launch_nc(bool cplx, bool half, unsigned grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b,
                       const CUtensorMap& c, const CUtensorMap& d, const TcParams& prm) {
-  if (cplx) gemm_tc_kernel<NC, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, c, d, prm);
-  else      gemm_tc_kernel<NC, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, c, d, prm);
+  if (half) {
+    if (cplx) gemm_tc_kernel<NC, true, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, c, d, prm);
+    else      gemm_tc_kernel<NC, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, c, d, prm);
+  } else {
+    if (cplx) gemm_tc_kernel<NC, true, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, c, d, prm);
+    else      gemm_tc_kernel<NC, false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, c, d, prm);
+  }
 }
 
-int launch_gemm_tc(const PlanImpl& p, const float* d_xhi, const float* d_xlo, int64_t n_rows_pad, int64_t n_rows_alloc,
+int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int64_t n_rows_pad, int64_t n_rows_alloc,
                    float* d_mag2, float* d_cplx, float* d_rowmax, cudaStream_t st) {
   GTC_REQUIRE(p.tmap_op_hi != nullptr, GTC_E_ARG, "plan was not created with the tcgen05 engine");
   CUtensorMap tm_xhi, tm_xlo;
-  int rc = encode_2d(&tm_xhi, d_xhi, (uint64_t)n_rows_alloc, (uint64_t)p.kp, TBM);
+  int rc = encode_2d(&tm_xhi, d_xhi, (uint64_t)n_rows_alloc, (uint64_t)p.kp, TBM, p.elem_bytes);
   if (rc != GTC_OK) return rc;
-  rc = encode_2d(&tm_xlo, d_xlo, (uint64_t)n_rows_alloc, (uint64_t)p.kp, TBM);
+  rc = encode_2d(&tm_xlo, d_xlo, (uint64_t)n_rows_alloc, (uint64_t)p.kp, TBM, p.elem_bytes);
   if (rc != GTC_OK) return rc;
   TcParams prm;
   prm.nc = pick_nc(p.n_out);
   prm.kb_per_split = p.tc_kb_per_split > 0 ? p.tc_kb_per_split : 8;
   prm.n_chunks = (int)ceil_div(p.n_out, prm.nc);
   prm.n_out = p.n_out;
-  prm.kb_per_part = p.kp / TBK;
+  prm.kb_per_part = p.kp / p.kb_elems;
+  prm.out_scale = p.out_scale;
   prm.parts = p.parts;
   prm.m_tiles = n_rows_pad / TBM;
   prm.mag2 = d_mag2; prm.cplx = d_cplx; prm.rowmax = d_rowmax;
@@ -398,12 +429,13 @@ int launch_gemm_tc(const PlanImpl& p, const float* d_xhi, const float* d_xlo, in
   const CUtensorMap& tm_ohi = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_hi);
   const CUtensorMap& tm_olo = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_lo);
   const bool cplx = d_cplx != nullptr;
+  const bool half = p.elem_bytes == 2;
   switch (prm.nc) {
-    case 256: launch_nc<256>(cplx, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
-    case 240: launch_nc<240>(cplx, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
-    case 192: launch_nc<192>(cplx, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
-    case 128: launch_nc<128>(cplx, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
-    default:  launch_nc<64>(cplx, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
+    case 256: launch_nc<256>(cplx, half, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
+    case 240: launch_nc<240>(cplx, half, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
+    case 192: launch_nc<192>(cplx, half, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
+    case 128: launch_nc<128>(cplx, half, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
+    default:  launch_nc<64>(cplx, half, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
   }
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;

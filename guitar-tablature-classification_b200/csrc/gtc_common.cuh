@@ -49,7 +49,9 @@ struct PlanImpl {
   int seg_len, seg_hop, n_bins, n_frames;
   int parts;        // P: audio rows per segment
   int row_len;      // samples per audio row (seg_hop when P>1 or seg_len when P==1)
-  int kp;           // row_len rounded up to 32 floats (one 128-byte swizzle atom)
+  int elem_bytes;   // operand element size: 4 (fp32 containers of the tf32 / SIMT engines) or 2 (fp16x2 engine)
+  int kb_elems;     // elements per 128-byte k-block: 32 (fp32) or 64 (fp16)
+  int kp;           // row_len rounded up to kb_elems (one 128-byte swizzle atom)
   int k_total;      // P * kp
   int n_out;        // 2 * n_bins * n_frames  (real operator rows)
   int n_pad;        // n_out rounded up to 128
@@ -57,20 +59,22 @@ struct PlanImpl {
   int sm_count;
   int tc_max_ctas;      // persistent GEMM grid limit (0 = sm_count)
   int tc_kb_per_split;  // K blocks per tensor-core accumulation split (0 = default), env GTC_TC_KSPLIT
-  float* d_op;      // [n_pad][k_total]  operator, fp32, K padded per part (SIMT engine)
-  float* d_op_hi;   // [n_pad][k_total]  tf32-representable high part (RN)
-  float* d_op_lo;   // [n_pad][k_total]  residual  A - hi
-  void* tmap_op_hi; // CUtensorMap storage (128 B each), engine TCGEN05 only
+  float x_scale;    // fp16x2 engine: audio is multiplied by this power of two before the hi/lo split (1 otherwise)
+  float out_scale;  // epilogue factor undoing x_scale and the operator's power-of-two scale (1 otherwise)
+  float* d_op;      // [n_pad][k_total]  operator, fp32, K padded per part (SIMT engine only)
+  void* d_op_hi;    // [n_pad][k_total]  high part: tf32-representable fp32 (RN) or fp16
+  void* d_op_lo;    // [n_pad][k_total]  residual of the high part, same element type
+  void* tmap_op_hi; // CUtensorMap storage (128 B each), tcgen05 engines only
   void* tmap_op_lo;
 };
 
-// launchers (each enqueues on `st`, returns a GTC_* code)
+// launchers (each enqueues on `st`, returns a GTC_* code); xhi/xlo element type follows PlanImpl::elem_bytes
 int launch_frame(const PlanImpl& p, const float* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
-                 int n_clips, int64_t n_rows, int64_t n_rows_alloc, float* d_xhi, float* d_xlo, float* d_rowmax,
+                 int n_clips, int64_t n_rows, int64_t n_rows_alloc, void* d_xhi, void* d_xlo, float* d_rowmax,
                  cudaStream_t st);
 int launch_gemm_simt(const PlanImpl& p, const float* d_xhi, const float* d_xlo, int64_t n_rows_pad,
                      float* d_mag2, float* d_cplx, float* d_rowmax, cudaStream_t st);
-int launch_gemm_tc(const PlanImpl& p, const float* d_xhi, const float* d_xlo, int64_t n_rows_pad, int64_t n_rows_alloc,
+int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int64_t n_rows_pad, int64_t n_rows_alloc,
                    float* d_mag2, float* d_cplx, float* d_rowmax, cudaStream_t st);
 int tc_plan_init(PlanImpl& p);
 void tc_plan_free(PlanImpl& p);

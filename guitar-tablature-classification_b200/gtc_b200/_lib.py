@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libgtc.so")
 
 GTC_GEMM_TCGEN05_3XTF32 = 0
 GTC_GEMM_SIMT_FP32 = 1
+GTC_GEMM_TCGEN05_FP16X2 = 2
 GTC_OPT_TC_KSPLIT = 1
 GTC_OPT_GEMM_MAX_CTAS = 2
 GTC_OPT_PATCH_MAX_CTAS = 16

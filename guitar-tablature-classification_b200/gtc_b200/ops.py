@@ -51,7 +51,7 @@ class CqtPlan:
         self.seg_hop = recipe.seg_hop if seg_hop is None else int(seg_hop)
         self.n_bins = recipe.n_bins
         self.n_frames = n_frames_of(recipe, self.seg_len)
-        self.engine = _lib.GTC_GEMM_TCGEN05_3XTF32 if engine is None else int(engine)
+        self.engine = _lib.GTC_GEMM_TCGEN05_FP16X2 if engine is None else int(engine)
         op = np.ascontiguousarray(get_operator(recipe, self.seg_len), dtype=np.float32)
         assert op.shape == (2 * self.n_bins * self.n_frames, self.seg_len)
         handle = C.c_void_p()

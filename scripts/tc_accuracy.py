@@ -15,9 +15,9 @@ co, so = torch.from_numpy(clip_off).to(dev), torch.from_numpy(seg_off).to(dev)
 n_seg = int(seg_off[-1])
 ref = ref_plan.segments_complex(audio, co, so, n_seg).cpu().numpy().astype(np.complex128)
 peak = np.abs(ref).max(axis=(1, 2), keepdims=True)
-for ks in (1000, 24, 12, 6, 3):
+for eng, ks in ((0, 1000), (0, 8), (2, 1000), (2, 16), (2, 8), (2, 4)):
     os.environ["GTC_TC_KSPLIT"] = str(ks)
-    p = ops.CqtPlan(r, engine=0)
+    p = ops.CqtPlan(r, engine=eng)
     got = p.segments_complex(audio, co, so, n_seg).cpu().numpy()
     err = np.abs(got - ref) / peak
     keep = np.abs(ref) > peak * 10 ** (-15.5 / 20)
@@ -28,6 +28,17 @@ for ks in (1000, 24, 12, 6, 3):
     a.record()
     for _ in range(5): p.segments_db(audio, co, so, n_seg, out=db)
     b.record(); torch.cuda.synchronize()
-    print(json.dumps({"ksplit": ks, "max_err_rel_peak": float(err.max()), "rms_err_rel_peak": float(np.sqrt((err ** 2).mean())),
+    print(json.dumps({"engine": eng, "ksplit": ks, "max_err_rel_peak": float(err.max()), "rms_err_rel_peak": float(np.sqrt((err ** 2).mean())),
                       "max_rel_mag_err_above_cut": float(rel.max()), "ms": a.elapsed_time(b) / 5, "n_seg": n_seg}))
+    p.close()
+
+# quiet audio (amplitude 2e-3): fp16 lo parts go subnormal -- check the scaling keeps precision
+audio_q = audio * 0.02
+refq = ref_plan.segments_complex(audio_q, co, so, n_seg).cpu().numpy().astype(np.complex128)
+peakq = np.abs(refq).max(axis=(1, 2), keepdims=True)
+os.environ["GTC_TC_KSPLIT"] = "8"
+for eng in (0, 2):
+    p = ops.CqtPlan(r, engine=eng)
+    got = p.segments_complex(audio_q, co, so, n_seg).cpu().numpy()
+    print(json.dumps({"quiet_engine": eng, "max_err_rel_peak": float((np.abs(got - refq) / peakq).max())}))
     p.close()

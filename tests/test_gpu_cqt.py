@@ -10,7 +10,7 @@ from oracle import cqt_oracle as co
 pytestmark = pytest.mark.gpu
 
 SR = 22050
-ENGINES = {"simt": 1, "tcgen05": 0}
+ENGINES = {"simt": 1, "tcgen05": 0, "fp16x2": 2}
 
 
 def oracle_segments(clips, recipe, cache):
@@ -121,11 +121,12 @@ def test_linearity_property_at_scale(plan):
 
 def test_engines_agree(recipe, lib, clips):
     from gtc_b200 import ops
-    p0, p1 = ops.CqtPlan(recipe, engine=0), ops.CqtPlan(recipe, engine=1)
-    a, b = run_gpu(p0, clips, True), run_gpu(p1, clips, True)
+    p0, p1, p2 = ops.CqtPlan(recipe, engine=0), ops.CqtPlan(recipe, engine=1), ops.CqtPlan(recipe, engine=2)
+    a, b, c = run_gpu(p0, clips, True), run_gpu(p1, clips, True), run_gpu(p2, clips, True)
     scale = np.abs(b).max(axis=(1, 2), keepdims=True)
     assert (np.abs(a - b) / scale).max() < 2e-5      # fp32 FMA chain (K = 4410) vs 3xTF32 + split accumulation
-    p0.close(); p1.close()
+    assert (np.abs(c - b) / scale).max() < 2e-5      # ... vs fp16x2 + split accumulation
+    p0.close(); p1.close(); p2.close()
 
 
 def test_non_overlapping_windows_44k(lib):
