@@ -237,8 +237,15 @@ def run_cuda_arm(args):
     on, du, pi, evt_off = synth.note_events([CLIP_SECONDS] * n_clips, seed=2 + rank)
     events_host = torch.from_numpy(np.stack([on, du, pi])).pin_memory()
     events_dev = events_host.to(dev)
-    audio_host = torch.empty(audio_dev.shape, dtype=torch.float32, pin_memory=True)
-    audio_host.copy_(audio_dev)
+    # The clips are 16-bit PCM WAV files in the reference's world (GuitarSet; librosa.load converts x/32768 to fp32,
+    # cqt.py:23).  Quantise the synthetic audio to PCM once; the device-resident arm gets the fp32 array librosa would
+    # return, the end-to-end arm uploads the file's int16 samples and converts on the device (identical values).
+    pcm_dev = torch.clamp(torch.round(audio_dev * 32768.0), -32768, 32767).to(torch.int16)
+    audio_dev = pcm_dev.to(torch.float32) / 32768.0
+    host_dtype = torch.float32 if args.host_audio == "f32" else torch.int16
+    audio_host = torch.empty(audio_dev.shape, dtype=host_dtype, pin_memory=True)
+    audio_host.copy_(audio_dev if args.host_audio == "f32" else pcm_dev)
+    del pcm_dev
     lens = np.full(n_clips, n, dtype=np.int64)
     fe = FrontEnd(recipe, device=local_rank, engine=args.engine, chunk_segments=args.chunk_segments, patch_batch=args.patch_batch,
                   overlap=args.overlap, gemm_ctas=args.gemm_ctas, patch_ctas_per_sm=args.patch_ctas_per_sm)
@@ -327,6 +334,7 @@ def run_cuda_arm(args):
                 "dtype": "f32", "data": "synthetic", "config": workload_config(n_clips),
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": out_e2e.h2d_bytes, "d2h_bytes_per_step": out_e2e.d2h_bytes,
+                        "host_audio": "int16 PCM (the WAV files' samples; x/32768 on the device == librosa.load)" if args.host_audio == "pcm16" else "fp32",
                         "note": "pinned host audio+events in, dB features + labels + stats back; patches stay in HBM for the engines"},
                 "gpu_launches": out_dev.launches * args.steps,
                 "roofline": {"bound": "hbm", "kernel": "patch_kernel<5> (gtc_patches)", "achieved": achieved, "peak": peak_hbm,
@@ -353,6 +361,7 @@ def main():
     ap.add_argument("--chunk-segments", type=int, default=16384)
     ap.add_argument("--patch-batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-audio", default="pcm16", choices=["pcm16", "f32"], help="sample type of the pinned host audio of the e2e arm")
     ap.add_argument("--engine", type=int, default=None, help="GEMM engine: 0 tcgen05 3xTF32, 1 SIMT fp32, 2 tcgen05 fp16x2 (default: library default)")
     ap.add_argument("--overlap", action="store_true", help="run each chunk's patch kernel beside the next chunk's GEMM (slower on B200, see profiles/)")
     ap.add_argument("--patch-ctas-per-sm", type=int, default=4, help="0 = do not limit the patch grid while overlapping")

@@ -203,10 +203,10 @@ extern "C" int gtc_cqt_workspace_bytes(const gtc_plan* plan, int64_t n_seg, int6
   return GTC_OK;
 }
 
-static int run_segments(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
+static int run_segments(const gtc_plan* plan, const void* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
                         int64_t n_clips, int64_t n_seg, float* d_out, bool complex_out, void* d_workspace,
                         size_t workspace_bytes, float power, float amin, float top_db, float cut_db, float floor_db,
-                        cudaStream_t st, int stages = 3 /* bit 0: framing, bit 1: contraction + finish */) {
+                        cudaStream_t st, int stages = 3 /* bit 0: framing, bit 1: contraction + finish */, int pcm16 = 0) {
   GTC_REQUIRE(plan != nullptr, GTC_E_ARG, "gtc_cqt_segments: plan is NULL");
   GTC_REQUIRE(n_clips >= 0 && n_seg >= 0, GTC_E_ARG, "gtc_cqt_segments: negative sizes");
   if (n_seg == 0) return GTC_OK;
@@ -228,7 +228,7 @@ static int run_segments(const gtc_plan* plan, const float* d_audio, const int64_
   float* gout = reinterpret_cast<float*>(ws + w.off_out);
   float* rowmax = reinterpret_cast<float*>(ws + w.off_rowmax);
   int rc = GTC_OK;
-  if (stages & 1) rc = launch_frame(p, d_audio, d_clip_off, d_seg_off, (int)n_clips, w.n_rows, w.n_rows_alloc, xhi, xlo, rowmax, st);
+  if (stages & 1) rc = launch_frame(p, d_audio, pcm16, d_clip_off, d_seg_off, (int)n_clips, w.n_rows, w.n_rows_alloc, xhi, xlo, rowmax, st);
   if (rc != GTC_OK || (stages & 2) == 0) return rc;
   float* mag2 = complex_out ? nullptr : gout;
   float* cplx = complex_out ? gout : nullptr;
@@ -254,6 +254,12 @@ extern "C" int gtc_cqt_frame(const gtc_plan* plan, const float* d_audio, const i
                              int64_t n_clips, int64_t n_seg, void* d_workspace, size_t workspace_bytes, gtc_stream_t stream) {
   return run_segments(plan, d_audio, d_clip_off, d_seg_off, n_clips, n_seg, nullptr, false, d_workspace, workspace_bytes,
                       4.f, 1e-5f, 80.f, -60.f, -120.f, (cudaStream_t)stream, 1);
+}
+
+extern "C" int gtc_cqt_frame_pcm16(const gtc_plan* plan, const int16_t* d_pcm, const int64_t* d_clip_off, const int64_t* d_seg_off,
+                                   int64_t n_clips, int64_t n_seg, void* d_workspace, size_t workspace_bytes, gtc_stream_t stream) {
+  return run_segments(plan, d_pcm, d_clip_off, d_seg_off, n_clips, n_seg, nullptr, false, d_workspace, workspace_bytes,
+                      4.f, 1e-5f, 80.f, -60.f, -120.f, (cudaStream_t)stream, 1, 1);
 }
 
 extern "C" int gtc_cqt_contract_db(const gtc_plan* plan, const int64_t* d_clip_off, const int64_t* d_seg_off, int64_t n_clips,

@@ -40,9 +40,14 @@ __device__ __forceinline__ void split_store(float* hi, float* lo, int64_t i, con
   reinterpret_cast<float4*>(lo)[i] = l;
 }
 
-template <typename T>
+// input sample types: fp32 (what librosa.load returns) or the WAV file's own 16-bit PCM, converted exactly as
+// librosa/soundfile do (x / 32768 in fp32, exact) -- half the host->device bytes of the end-to-end path
+__device__ __forceinline__ float load_sample(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_sample(const int16_t* p) { return (float)__ldg(p) * (1.f / 32768.f); }
+
+template <typename T, typename In>
 __global__ void __launch_bounds__(256)
-frame_kernel(const float* __restrict__ audio, const int64_t* __restrict__ clip_off, const int64_t* __restrict__ seg_off,
+frame_kernel(const In* __restrict__ audio, const int64_t* __restrict__ clip_off, const int64_t* __restrict__ seg_off,
              int n_clips, int parts, int row_len, int seg_hop, int kp, int64_t n_rows, int64_t n_rows_alloc,
              T* __restrict__ xhi, T* __restrict__ xlo, float scale, float* __restrict__ rowmax, int64_t n_rowmax) {
   const int vec_per_row = kp >> 2;
@@ -63,31 +68,40 @@ frame_kernel(const float* __restrict__ audio, const int64_t* __restrict__ clip_o
       const int64_t base = __ldg(clip_off + lo) + r * seg_hop + k0;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (k0 + j < row_len && base + j < clip_end) v[j] = __ldg(audio + base + j);
+        if (k0 + j < row_len && base + j < clip_end) v[j] = load_sample(audio + base + j);
     }
     split_store(xhi, xlo, i, v, scale);
     if (k0 == 0 && row < n_rowmax) rowmax[row] = 0.f;
   }
 }
 
-int launch_frame(const PlanImpl& p, const float* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
-                 int n_clips, int64_t n_rows, int64_t n_rows_alloc, void* d_xhi, void* d_xlo, float* d_rowmax,
-                 cudaStream_t st) {
+template <typename In>
+static int launch_frame_t(const PlanImpl& p, const In* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
+                          int n_clips, int64_t n_rows, int64_t n_rows_alloc, void* d_xhi, void* d_xlo, float* d_rowmax,
+                          cudaStream_t st) {
   const int64_t total = n_rows_alloc * (p.kp / 4);
   int64_t blocks = ceil_div(total, 256);
   const int64_t cap = (int64_t)p.sm_count * 16;
   if (blocks > cap) blocks = cap;
   const int64_t n_rowmax = round_up(n_rows, 128);
   if (p.elem_bytes == 2)
-    frame_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(d_audio, d_clip_off, d_seg_off, n_clips, p.parts, p.row_len,
+    frame_kernel<__half, In><<<(unsigned)blocks, 256, 0, st>>>(d_audio, d_clip_off, d_seg_off, n_clips, p.parts, p.row_len,
                                                           p.seg_hop, p.kp, n_rows, n_rows_alloc, (__half*)d_xhi, (__half*)d_xlo,
                                                           p.x_scale, d_rowmax, n_rowmax);
   else
-    frame_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(d_audio, d_clip_off, d_seg_off, n_clips, p.parts, p.row_len,
+    frame_kernel<float, In><<<(unsigned)blocks, 256, 0, st>>>(d_audio, d_clip_off, d_seg_off, n_clips, p.parts, p.row_len,
                                                          p.seg_hop, p.kp, n_rows, n_rows_alloc, (float*)d_xhi, (float*)d_xlo,
                                                          1.f, d_rowmax, n_rowmax);
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;
+}
+
+int launch_frame(const PlanImpl& p, const void* d_audio, int pcm16, const int64_t* d_clip_off, const int64_t* d_seg_off,
+                 int n_clips, int64_t n_rows, int64_t n_rows_alloc, void* d_xhi, void* d_xlo, float* d_rowmax,
+                 cudaStream_t st) {
+  if (pcm16)
+    return launch_frame_t(p, (const int16_t*)d_audio, d_clip_off, d_seg_off, n_clips, n_rows, n_rows_alloc, d_xhi, d_xlo, d_rowmax, st);
+  return launch_frame_t(p, (const float*)d_audio, d_clip_off, d_seg_off, n_clips, n_rows, n_rows_alloc, d_xhi, d_xlo, d_rowmax, st);
 }
 
 // one warp per segment

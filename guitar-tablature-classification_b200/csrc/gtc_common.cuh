@@ -69,7 +69,7 @@ struct PlanImpl {
 };
 
 // launchers (each enqueues on `st`, returns a GTC_* code); xhi/xlo element type follows PlanImpl::elem_bytes
-int launch_frame(const PlanImpl& p, const float* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
+int launch_frame(const PlanImpl& p, const void* d_audio, int pcm16, const int64_t* d_clip_off, const int64_t* d_seg_off,
                  int n_clips, int64_t n_rows, int64_t n_rows_alloc, void* d_xhi, void* d_xlo, float* d_rowmax,
                  cudaStream_t st);
 int launch_gemm_simt(const PlanImpl& p, const float* d_xhi, const float* d_xlo, int64_t n_rows_pad,

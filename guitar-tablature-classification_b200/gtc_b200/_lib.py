@@ -33,6 +33,7 @@ PROTOTYPES = {
     "gtc_cqt_workspace_bytes": (_i, [_vp, _i64, _i64, C.POINTER(_sz)]),
     "gtc_cqt_segments_db": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp]),
     "gtc_cqt_frame": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz, _vp]),
+    "gtc_cqt_frame_pcm16": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz, _vp]),
     "gtc_cqt_contract_db": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp]),
     "gtc_set_option": (_i, [_i, _i]),
     "gtc_cqt_segments_complex": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),

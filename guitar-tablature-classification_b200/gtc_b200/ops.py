@@ -98,20 +98,30 @@ class CqtPlan:
         """audio: concatenated mono fp32 clips (device); returns [n_seg, n_bins, T] fp32 dB features
         (== np.stack of what cqt.py:58 saves per segment)."""
         _need_cuda(audio, clip_off, seg_off)
-        assert audio.dtype == torch.float32 and clip_off.dtype == torch.int64 and seg_off.dtype == torch.int64
+        assert audio.dtype in (torch.float32, torch.int16) and clip_off.dtype == torch.int64 and seg_off.dtype == torch.int64
         n_clips = clip_off.numel() - 1
         if out is None:
             out = torch.empty((n_seg, self.n_bins, self.n_frames), dtype=torch.float32, device=audio.device)
         ws = self.workspace(n_seg, n_clips) if workspace is None else workspace
         r = self.recipe
+        if audio.dtype == torch.int16:                       # 16-bit PCM straight from the WAV file
+            if n_seg:
+                self.frame(audio, clip_off, seg_off, n_seg, ws)
+                self.contract_db(clip_off, seg_off, n_seg, out, ws)
+            return out
         _lib.check(_lib.load().gtc_cqt_segments_db(self._h, _ptr(audio), _ptr(clip_off), _ptr(seg_off), n_clips, n_seg,
                                                    _ptr(out), _ptr(ws), ws.numel(), r.power, r.amin, r.top_db, r.cut_db,
                                                    r.floor_db, _stream()), "gtc_cqt_segments_db")
         return out
 
     def frame(self, audio: torch.Tensor, clip_off: torch.Tensor, seg_off: torch.Tensor, n_seg: int, workspace: torch.Tensor) -> None:
-        """Stage 1 of segments_db: audio -> tf32 hi/lo row matrix in the workspace."""
+        """Stage 1 of segments_db: audio (fp32, or the file's int16 PCM) -> hi/lo operand row matrix in the workspace."""
         _need_cuda(audio, clip_off, seg_off, workspace)
+        if audio.dtype == torch.int16:
+            _lib.check(_lib.load().gtc_cqt_frame_pcm16(self._h, _ptr(audio), _ptr(clip_off), _ptr(seg_off), clip_off.numel() - 1,
+                                                       n_seg, _ptr(workspace), workspace.numel(), _stream()), "gtc_cqt_frame_pcm16")
+            return
+        assert audio.dtype == torch.float32
         _lib.check(_lib.load().gtc_cqt_frame(self._h, _ptr(audio), _ptr(clip_off), _ptr(seg_off), clip_off.numel() - 1, n_seg,
                                              _ptr(workspace), workspace.numel(), _stream()), "gtc_cqt_frame")
 

@@ -22,9 +22,10 @@ from .cqt_design import CqtRecipe
 
 @dataclass
 class ShardInputs:
-    """One shard.  ``audio`` is the concatenation of all clips (fp32, 1-D): pinned host memory for the end-to-end
-    path or a CUDA tensor for the device-resident path.  Events are fp64 arrays concatenated per clip."""
-    audio: torch.Tensor            # [n_samples] fp32
+    """One shard.  ``audio`` is the concatenation of all clips (1-D; fp32 as librosa.load returns it, or the WAV files'
+    own int16 PCM, converted on the device exactly as librosa does): pinned host memory for the end-to-end path or a
+    CUDA tensor for the device-resident path.  Events are fp64 arrays concatenated per clip."""
+    audio: torch.Tensor            # [n_samples] fp32 or int16
     clip_lens: np.ndarray          # [n_clips] int64 (host)
     events: torch.Tensor           # [3, n_evt] fp64 rows = onset, duration, pitch (pinned host or CUDA, like audio)
     evt_off: np.ndarray            # [n_clips+1] int64 (host)
@@ -208,13 +209,13 @@ class FrontEnd:
                         d_ev = inp.events[:, ch.e0:ch.e1]
                         d_on, d_du, d_pi = d_ev[0], d_ev[1], d_ev[2]
                     else:
-                        d_audio = self._buf(f"audio{b}", (max_samples,), torch.float32)[:ns]
+                        d_audio = self._buf(f"audio{b}", (max_samples,), inp.audio.dtype)[:ns]
                         d_audio.copy_(inp.audio[ch.s0:ch.s1], non_blocking=True)
                         d_evb = self._buf(f"ev{b}", (3, max_evt), torch.float64)
                         for j in range(3):                            # contiguous row slices -> plain async memcpys
                             d_evb[j, :ne].copy_(inp.events[j, ch.e0:ch.e1], non_blocking=True)
                         d_on, d_du, d_pi = d_evb[0, :ne], d_evb[1, :ne], d_evb[2, :ne]
-                        out.h2d_bytes += ns * 4 + ne * 24
+                        out.h2d_bytes += ns * inp.audio.element_size() + ne * 24
                     ev_in = torch.cuda.Event()
                     ev_in.record(self.s_copy)
                 d_clip_off, d_seg_off, d_evt_off = d_meta[: nc + 1], d_meta[nc + 1: 2 * nc + 2], d_meta[2 * nc + 2:]

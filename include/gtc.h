@@ -91,6 +91,11 @@ int gtc_cqt_segments_db(const gtc_plan* plan, const float* d_audio, const int64_
  * chunk's patch kernel exactly when the next GEMM becomes runnable, so the two share the GPU. */
 int gtc_cqt_frame(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
                   int64_t n_clips, int64_t n_seg, void* d_workspace, size_t workspace_bytes, gtc_stream_t stream);
+/* gtc_cqt_frame for the WAV file's own 16-bit PCM samples (mono, already channel-averaged if needed): the kernel converts
+ * x / 32768 in fp32 exactly as librosa.load(sr=None) does for PCM_16 files (/root/reference/cqt.py:23), so the result is
+ * identical to uploading the fp32 array at half the host->device bytes. */
+int gtc_cqt_frame_pcm16(const gtc_plan* plan, const int16_t* d_pcm, const int64_t* d_clip_off, const int64_t* d_seg_off,
+                        int64_t n_clips, int64_t n_seg, void* d_workspace, size_t workspace_bytes, gtc_stream_t stream);
 int gtc_cqt_contract_db(const gtc_plan* plan, const int64_t* d_clip_off, const int64_t* d_seg_off, int64_t n_clips,
                         int64_t n_seg, float* d_out_db, void* d_workspace, size_t workspace_bytes,
                         float power, float amin, float top_db, float cut_db, float floor_db, gtc_stream_t stream);

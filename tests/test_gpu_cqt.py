@@ -143,3 +143,15 @@ def test_non_overlapping_windows_44k(lib):
         ok = np.abs(pre + 60) > 0.02
         assert np.abs(got[i] - want)[ok].max() < 0.01
     plan.close()
+
+
+def test_pcm16_input_is_bit_identical_to_librosa_fp32(plan, clips):
+    """int16 PCM uploaded as-is and converted on the device (x/32768) == the fp32 array librosa.load returns (cqt.py:23)."""
+    dev = torch.device("cuda")
+    pcm = [np.clip(np.round(c.astype(np.float64) * 32768.0), -32768, 32767).astype(np.int16) for c in clips]
+    as_f32 = [p.astype(np.float32) / np.float32(32768.0) for p in pcm]
+    want = run_gpu(plan, as_f32)
+    clip_off, seg_off = plan.offsets([len(c) for c in pcm])
+    got = plan.segments_db(torch.from_numpy(np.concatenate(pcm)).to(dev), torch.from_numpy(clip_off).to(dev),
+                           torch.from_numpy(seg_off).to(dev), int(seg_off[-1])).cpu().numpy()
+    assert np.array_equal(got, want)
