@@ -1,0 +1,460 @@
+// Structured (multirate) CQT of variable-length segments: librosa.cqt evaluated the way librosa itself does it --
+// a chain of soxr-HQ 2:1 decimations and, per octave, the wavelet basis applied to centred, zero-padded frames --
+// instead of the collapsed segment operator of cqt_api.cu.  It serves the recipes whose operator would not fit
+// (/root/reference/tablature_generator.py:616-620: 3 s segments -> 21 840 x 66 150), whole-clip CQTs and arbitrary
+// sample rates, and it is the on-device cross-check of the tensor-core operator path.
+//
+//   decimate2_kernel  : y_{i+1}[k] = sum_j h[j] * y_i[2k + c - j]      (taps in shared memory, even/odd input phases
+//                       de-interleaved into two shared arrays so a warp reads unit-stride; zero-extended signal,
+//                       group delay compensated, length ceil(n/2), sqrt(2) gain folded into h)
+//                       == librosa.resample(orig_sr=2, target_sr=1, res_type='soxr_hq', scale=True)
+//   response_kernel   : C[bin, t] = sum_n W_i[bin, n] * ypad_i[t*hop_i + n]   (the octave's time-domain filters
+//                       W_i = fft_basis_i @ rfft-matrix, designed on the host; frames x basis contraction, fp32 FMA;
+//                       32 frames x n_fft staged in shared memory per CTA, each thread owns 1 frame x 2 complex bins)
+//                       == librosa.stft(window='ones', center=True, pad_mode='constant') followed by fft_basis.dot(D)
+//   finish_kernel     : |C|^power -> amplitude_to_db(ref=max over the segment, amin, top_db) -> cut   (in place)
+//
+// Everything is HBM/L2-bound streaming work except the FIR (389 taps), which is shared-memory bound.
+#include <math.h>
+#include <new>
+#include <vector>
+#include "gtc_common.cuh"
+
+namespace gtc {
+
+constexpr int kMaxOctaves = 16;
+constexpr int kDecTile = 1024;      // outputs per CTA of the decimator (256 threads x 4)
+constexpr int kFramesPerCta = 32;
+
+struct SPlanImpl {
+  int device, sm_count;
+  int n_oct, n_fft, hop, n_bins, n_filters, n_taps;
+  int groups;               // float4 groups of the 2*n_filters real outputs of one octave
+  int bin_lo[kMaxOctaves];  // first output bin of octave i (octave 0 = top octave)
+  int bin_cnt[kMaxOctaves];
+  float* d_filters;         // [n_oct][n_fft][groups*4]: sample-major so a thread fetches its 4 outputs as one float4
+  float* d_taps;            // [n_taps], sqrt(2) gain folded in
+};
+
+struct OctaveBufs {
+  int64_t off[kMaxOctaves];     // float offset of octave i's signals inside the workspace (i >= 1)
+  int64_t stride[kMaxOctaves];  // floats per segment
+};
+
+__device__ __forceinline__ float s_load(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float s_load(const int16_t* p) { return (float)__ldg(p) * (1.f / 32768.f); }
+
+__device__ __forceinline__ int halved(int n, int times) {
+  for (int i = 0; i < times; ++i) n = (n + 1) >> 1;
+  return n;
+}
+
+// frames librosa keeps (__trim_stack): min over octaves of 1 + len_i // hop_i
+__device__ __host__ __forceinline__ int frames_of(int len, int hop, int n_oct) {
+  int t = 0x7fffffff;
+  for (int i = 0; i < n_oct; ++i) {
+    const int f = 1 + len / hop;
+    t = f < t ? f : t;
+    if ((hop & 1) == 0) { hop >>= 1; len = (len + 1) >> 1; }
+  }
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 2:1 decimator.  blockIdx.x = segment * tiles + tile.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename In>
+__global__ void __launch_bounds__(256)
+decimate2_kernel(const In* __restrict__ src, const int64_t* __restrict__ seg_start, const int32_t* __restrict__ seg_valid,
+                 const int32_t* __restrict__ seg_len, int stage, int64_t src_stride, float* __restrict__ dst,
+                 int64_t dst_stride, const float* __restrict__ taps, int n_taps, int tiles) {
+  extern __shared__ float sm[];
+  const int c = (n_taps - 1) >> 1;                 // even: n_taps == 1 (mod 4)
+  const int span = kDecTile + c + 1;
+  float* sh = sm;                                  // [n_taps + 1]
+  float* xe = sh + ((n_taps + 4) & ~3);            // even-phase inputs
+  float* xo = xe + ((span + 3) & ~3);              // odd-phase inputs
+  const int64_t s = blockIdx.x / tiles;
+  const int tile = blockIdx.x - (int)(s * tiles);
+  const int len_in = halved(__ldg(seg_len + s), stage);
+  const int len_out = (len_in + 1) >> 1;
+  const int k0 = tile * kDecTile;
+  if (k0 >= len_out) return;
+  const int readable = stage == 0 ? min(len_in, __ldg(seg_valid + s)) : len_in;
+  const In* x = src + (seg_start ? __ldg(seg_start + s) : s * src_stride);
+
+  for (int j = threadIdx.x; j < n_taps; j += blockDim.x) sh[j] = __ldg(taps + j);
+  if (threadIdx.x == 0) sh[n_taps] = 0.f;
+  const int base = 2 * k0 - c;                     // input index of xe[0]
+  for (int m = threadIdx.x; m < 2 * span; m += blockDim.x) {
+    const int i = base + m;
+    const float v = (i >= 0 && i < readable) ? s_load(x + i) : 0.f;
+    if (m & 1) xo[m >> 1] = v; else xe[m >> 1] = v;
+  }
+  __syncthreads();
+
+  // out[k0+u] = sum_a h[2a] * xe[u + c - a] + h[2a+1] * xo[u + c - a - 1]
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int u0 = threadIdx.x;
+  const float* pe = xe + u0 + c;
+  const float* po = xo + u0 + c - 1;
+#pragma unroll 4
+  for (int a = 0; a < c; ++a) {
+    const float he = sh[2 * a], ho = sh[2 * a + 1];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      acc[r] = fmaf(he, pe[r * 256 - a], acc[r]);
+      acc[r] = fmaf(ho, po[r * 256 - a], acc[r]);
+    }
+  }
+  {
+    const float he = sh[2 * c];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = fmaf(he, pe[r * 256 - c], acc[r]);
+  }
+  float* y = dst + s * dst_stride;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int k = k0 + u0 + r * 256;
+    if (k < len_out) y[k] = acc[r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Octave response.  blockIdx.x covers 32 consecutive global frames q = segment * t_max + t.
+// blockDim = 32 * groups: lane = frame slot, warp = output group (4 real outputs = 2 complex bins).
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename In>
+__global__ void __launch_bounds__(1024)
+response_kernel(const In* __restrict__ src, const int64_t* __restrict__ seg_start, const int32_t* __restrict__ seg_valid,
+                const int32_t* __restrict__ seg_len, int64_t n_seg, int octave, int n_oct, int hop0, int64_t src_stride,
+                const float* __restrict__ filters, int n_fft, int groups, int bin_lo, int bin_cnt, int n_bins, int t_max,
+                float* __restrict__ out, int complex_out, float* __restrict__ segmax) {
+  extern __shared__ float sm[];
+  const int fstride = n_fft + 1;
+  float4* w4 = reinterpret_cast<float4*>(sm);                       // [n_fft][groups]
+  float* fr = sm + (size_t)n_fft * groups * 4;                      // [32][n_fft + 1]
+  int* meta = reinterpret_cast<int*>(fr + kFramesPerCta * fstride); // seg_lo, seg_hi, t, readable, valid, max  (x32)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const int hop = hop0 >> octave;
+
+  if (warp == 0) {
+    const int64_t q = (int64_t)blockIdx.x * kFramesPerCta + lane;
+    const int64_t s = q / t_max;
+    const int t = (int)(q - s * t_max);
+    int valid = 0, readable = 0;
+    if (s < n_seg) {
+      const int len0 = __ldg(seg_len + s);
+      const int len = halved(len0, octave);
+      readable = octave == 0 ? min(len, __ldg(seg_valid + s)) : len;
+      valid = t < frames_of(len0, hop0, n_oct);
+    }
+    meta[lane] = (int)(s & 0xffffffff);
+    meta[32 + lane] = (int)(s >> 32);
+    meta[64 + lane] = t;
+    meta[96 + lane] = readable;
+    meta[128 + lane] = valid;
+    meta[160 + lane] = 0;
+  }
+  const float4* gw = reinterpret_cast<const float4*>(filters) + (size_t)octave * n_fft * groups;
+  for (int i = threadIdx.x; i < n_fft * groups; i += blockDim.x) w4[i] = __ldg(gw + i);
+  __syncthreads();
+  for (int f = warp; f < kFramesPerCta; f += n_warps) {
+    float* row = fr + f * fstride;
+    if (!meta[128 + f]) {
+      for (int n = lane; n < n_fft; n += 32) row[n] = 0.f;
+      continue;
+    }
+    const int64_t s = ((int64_t)meta[32 + f] << 32) | (uint32_t)meta[f];
+    const In* x = src + (seg_start ? __ldg(seg_start + s) : s * src_stride);
+    const int first = meta[64 + f] * hop - (n_fft >> 1);
+    const int readable = meta[96 + f];
+    for (int n = lane; n < n_fft; n += 32) {
+      const int i = first + n;
+      row[n] = (i >= 0 && i < readable) ? s_load(x + i) : 0.f;
+    }
+  }
+  __syncthreads();
+
+  const float* row = fr + lane * fstride;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int n = 0; n < n_fft; ++n) {
+    const float xv = row[n];
+    const float4 w = w4[n * groups + warp];
+    acc.x = fmaf(xv, w.x, acc.x);
+    acc.y = fmaf(xv, w.y, acc.y);
+    acc.z = fmaf(xv, w.z, acc.z);
+    acc.w = fmaf(xv, w.w, acc.w);
+  }
+  const int valid = meta[128 + lane];
+  const int64_t s = ((int64_t)meta[32 + lane] << 32) | (uint32_t)meta[lane];
+  const int t = meta[64 + lane];
+  const int b0 = 2 * warp, b1 = 2 * warp + 1;
+  if (s < n_seg) {
+    if (complex_out) {
+      float2* o = reinterpret_cast<float2*>(out) + (s * n_bins) * t_max + t;
+      if (b0 < bin_cnt) o[(int64_t)(bin_lo + b0) * t_max] = valid ? make_float2(acc.x, acc.y) : make_float2(0.f, 0.f);
+      if (b1 < bin_cnt) o[(int64_t)(bin_lo + b1) * t_max] = valid ? make_float2(acc.z, acc.w) : make_float2(0.f, 0.f);
+    } else {
+      const float m0 = valid ? fmaf(acc.x, acc.x, acc.y * acc.y) : 0.f;
+      const float m1 = valid ? fmaf(acc.z, acc.z, acc.w * acc.w) : 0.f;
+      float* o = out + (s * n_bins) * t_max + t;
+      if (b0 < bin_cnt) o[(int64_t)(bin_lo + b0) * t_max] = m0;
+      if (b1 < bin_cnt) o[(int64_t)(bin_lo + b1) * t_max] = m1;
+      float m = 0.f;
+      if (b0 < bin_cnt) m = m0;
+      if (b1 < bin_cnt) m = fmaxf(m, m1);
+      if (valid) atomicMax(meta + 160 + lane, __float_as_int(m));       // m >= 0: int order == float order
+    }
+  }
+  if (!complex_out) {
+    __syncthreads();
+    if (warp == 0) {
+      // one global atomic per run of equal segments inside the CTA's 32 consecutive frames
+      const bool live = valid && s < n_seg;
+      const int mine = live ? meta[160 + lane] : 0;
+      const int64_t key = live ? s : (int64_t)(-1 - lane);      // frames past a segment's T separate the runs
+      const int64_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+      const bool head = lane == 0 || prev != key;
+      int best = mine;
+      for (int d = 1; d < 32; ++d) {
+        const int64_t ko = __shfl_down_sync(0xffffffffu, key, d);
+        const int vo = __shfl_down_sync(0xffffffffu, mine, d);
+        if (lane + d < 32 && ko == key) best = max(best, vo);
+      }
+      if (head && live) atomicMax(reinterpret_cast<int*>(segmax) + s, best);
+    }
+  }
+}
+
+// in-place |C|^2 -> dB  (same arithmetic as finish_db_kernel of cqt_frame_finish.cu)
+__global__ void __launch_bounds__(256)
+sfinish_kernel(float* __restrict__ io, const float* __restrict__ segmax, int64_t n_seg, int per_seg, float power,
+               float amin, float top_db, float cut_db, float floor_db) {
+  const float amin2 = amin * amin;
+  const int64_t total = n_seg * per_seg;
+  auto s_of = [&](float m2) -> float {
+    if (power == 4.f) return m2 * m2;
+    if (power == 2.f) return m2;
+    if (power == 1.f) return sqrtf(m2);
+    return powf(m2, 0.5f * power);
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / per_seg;
+    const float ref = s_of(__ldg(segmax + s));
+    const float ref_db = 10.f * log10f(fmaxf(amin2, ref * ref));
+    const float v = s_of(io[i]);
+    float db = 10.f * log10f(fmaxf(amin2, v * v)) - ref_db;
+    db = fmaxf(db, 0.f - top_db);
+    if (db < cut_db) db = floor_db;
+    io[i] = db;
+  }
+}
+
+struct SWorkspace {
+  OctaveBufs bufs;
+  size_t off_segmax, total;
+};
+
+static SWorkspace s_layout(const SPlanImpl& p, int64_t n_seg, int64_t max_len) {
+  SWorkspace w;
+  memset(&w, 0, sizeof(w));
+  size_t o = 0;
+  auto take = [&](size_t b) { size_t at = o; o += (b + 1023) & ~(size_t)1023; return at; };
+  w.off_segmax = take((size_t)(n_seg > 0 ? n_seg : 1) * sizeof(float));
+  int64_t len = max_len;
+  for (int i = 1; i < p.n_oct; ++i) {
+    len = (len + 1) / 2;
+    w.bufs.stride[i] = round_up(len, 4);
+    w.bufs.off[i] = (int64_t)(take((size_t)n_seg * w.bufs.stride[i] * sizeof(float)) / sizeof(float));
+  }
+  w.total = o;
+  return w;
+}
+
+template <typename In>
+static int run_structured(const SPlanImpl& p, const In* d_audio, const int64_t* d_seg_start, const int32_t* d_seg_valid,
+                          const int32_t* d_seg_len, int64_t n_seg, int64_t max_len, float* d_out, bool complex_out,
+                          char* ws, const SWorkspace& w, float power, float amin, float top_db, float cut_db,
+                          float floor_db, cudaStream_t st) {
+  float* wsf = reinterpret_cast<float*>(ws);
+  float* segmax = reinterpret_cast<float*>(ws + w.off_segmax);
+  const int t_max = frames_of((int)max_len, p.hop, p.n_oct);
+  if (!complex_out) GTC_CUDA_CHECK(cudaMemsetAsync(segmax, 0, (size_t)n_seg * sizeof(float), st));
+
+  // decimation chain: octave i+1 from octave i
+  const int c = (p.n_taps - 1) / 2;
+  const size_t dec_smem = (size_t)(((p.n_taps + 4) & ~3) + 2 * ((kDecTile + c + 1 + 3) & ~3)) * sizeof(float);
+  int64_t len = max_len;
+  for (int i = 0; i + 1 < p.n_oct; ++i) {
+    const int64_t out_len = (len + 1) / 2;
+    const int tiles = (int)ceil_div(out_len, kDecTile);
+    const int64_t blocks = n_seg * tiles;
+    GTC_REQUIRE(blocks < 0x7fffffffLL, GTC_E_ARG, "gtc_scqt: too many decimator tiles (%lld); split the batch", (long long)blocks);
+    float* dst = wsf + w.bufs.off[i + 1];
+    if (i == 0)
+      decimate2_kernel<In><<<(unsigned)blocks, 256, dec_smem, st>>>(d_audio, d_seg_start, d_seg_valid, d_seg_len, 0, 0, dst,
+                                                                     w.bufs.stride[1], p.d_taps, p.n_taps, tiles);
+    else
+      decimate2_kernel<float><<<(unsigned)blocks, 256, dec_smem, st>>>(wsf + w.bufs.off[i], nullptr, d_seg_valid, d_seg_len, i,
+                                                                        w.bufs.stride[i], dst, w.bufs.stride[i + 1], p.d_taps,
+                                                                        p.n_taps, tiles);
+    GTC_CUDA_CHECK(cudaGetLastError());
+    len = out_len;
+  }
+
+  const size_t resp_smem = ((size_t)p.n_fft * p.groups * 4 + (size_t)kFramesPerCta * (p.n_fft + 1) + 192) * sizeof(float);
+  const int64_t rblocks = ceil_div(n_seg * t_max, kFramesPerCta);
+  GTC_REQUIRE(rblocks < 0x7fffffffLL, GTC_E_ARG, "gtc_scqt: too many frames (%lld blocks); split the batch", (long long)rblocks);
+  for (int i = 0; i < p.n_oct; ++i) {
+    if (i == 0)
+      response_kernel<In><<<(unsigned)rblocks, 32 * p.groups, resp_smem, st>>>(
+          d_audio, d_seg_start, d_seg_valid, d_seg_len, n_seg, 0, p.n_oct, p.hop, 0, p.d_filters, p.n_fft, p.groups, p.bin_lo[0],
+          p.bin_cnt[0], p.n_bins, t_max, d_out, complex_out ? 1 : 0, segmax);
+    else
+      response_kernel<float><<<(unsigned)rblocks, 32 * p.groups, resp_smem, st>>>(
+          wsf + w.bufs.off[i], nullptr, d_seg_valid, d_seg_len, n_seg, i, p.n_oct, p.hop, w.bufs.stride[i], p.d_filters, p.n_fft,
+          p.groups, p.bin_lo[i], p.bin_cnt[i], p.n_bins, t_max, d_out, complex_out ? 1 : 0, segmax);
+    GTC_CUDA_CHECK(cudaGetLastError());
+  }
+  if (complex_out) return GTC_OK;
+  const int per_seg = p.n_bins * t_max;
+  int64_t fblocks = ceil_div(n_seg * per_seg, 256 * 4);
+  const int64_t cap = (int64_t)p.sm_count * 16;
+  if (fblocks > cap) fblocks = cap;
+  if (fblocks < 1) fblocks = 1;
+  sfinish_kernel<<<(unsigned)fblocks, 256, 0, st>>>(d_out, segmax, n_seg, per_seg, power, amin, top_db, cut_db, floor_db);
+  GTC_CUDA_CHECK(cudaGetLastError());
+  return GTC_OK;
+}
+
+}  // namespace gtc
+
+using namespace gtc;
+
+struct gtc_splan {
+  SPlanImpl impl;
+};
+
+extern "C" int gtc_scqt_frames(int64_t seg_len, int hop_length, int n_octaves) {
+  if (seg_len < 0 || seg_len > 0x7fffffffLL || hop_length <= 0 || n_octaves <= 0 || n_octaves > kMaxOctaves) return GTC_E_ARG;
+  return frames_of((int)seg_len, hop_length, n_octaves);
+}
+
+extern "C" int gtc_scqt_plan_create(gtc_splan** out, int device, int n_octaves, int n_fft, int hop_length, int n_bins,
+                                    int filters_per_octave, const float* h_filters, const float* h_taps, int n_taps) {
+  GTC_REQUIRE(out != nullptr, GTC_E_ARG, "gtc_scqt_plan_create: out is NULL");
+  *out = nullptr;
+  GTC_REQUIRE(h_filters && h_taps, GTC_E_ARG, "gtc_scqt_plan_create: NULL filter/tap table (design them with gtc_b200.cqt_design)");
+  GTC_REQUIRE(n_octaves > 0 && n_octaves <= kMaxOctaves, GTC_E_UNSUP, "gtc_scqt_plan_create: 1..%d octaves supported", kMaxOctaves);
+  GTC_REQUIRE(n_fft >= 32 && (n_fft & (n_fft - 1)) == 0 && n_fft <= 4096, GTC_E_UNSUP, "gtc_scqt_plan_create: n_fft must be a power of two in [32, 4096]");
+  GTC_REQUIRE(n_bins > 0 && filters_per_octave > 0 && filters_per_octave <= 64, GTC_E_UNSUP, "gtc_scqt_plan_create: 1..64 filters per octave supported");
+  GTC_REQUIRE(n_bins <= filters_per_octave * n_octaves && n_bins > filters_per_octave * (n_octaves - 1), GTC_E_ARG,
+              "gtc_scqt_plan_create: n_bins inconsistent with octaves x filters");
+  GTC_REQUIRE(hop_length > 0 && hop_length % (1 << (n_octaves - 1)) == 0, GTC_E_ARG,
+              "gtc_scqt_plan_create: hop_length must be a multiple of 2^(n_octaves-1) (librosa's own requirement)");
+  GTC_REQUIRE(n_taps >= 5 && n_taps % 4 == 1 && n_taps <= 4097, GTC_E_UNSUP, "gtc_scqt_plan_create: n_taps must be 1 (mod 4), <= 4097");
+  GTC_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GTC_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  GTC_REQUIRE(prop.major == 10, GTC_E_UNSUP, "libgtc is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+
+  gtc_splan* plan = new (std::nothrow) gtc_splan();
+  GTC_REQUIRE(plan != nullptr, GTC_E_NOMEM, "gtc_scqt_plan_create: out of host memory");
+  SPlanImpl& p = plan->impl;
+  memset(&p, 0, sizeof(p));
+  p.device = device; p.sm_count = prop.multiProcessorCount;
+  p.n_oct = n_octaves; p.n_fft = n_fft; p.hop = hop_length; p.n_bins = n_bins; p.n_filters = filters_per_octave; p.n_taps = n_taps;
+  p.groups = (2 * filters_per_octave + 3) / 4;
+  for (int i = 0; i < n_octaves; ++i) {            // librosa.vqt: octave i owns the top-most remaining filters
+    const int hi = n_bins - filters_per_octave * i;
+    const int lo = hi - filters_per_octave > 0 ? hi - filters_per_octave : 0;
+    p.bin_lo[i] = lo; p.bin_cnt[i] = hi - lo;
+  }
+  const size_t resp_smem = ((size_t)p.n_fft * p.groups * 4 + (size_t)kFramesPerCta * (p.n_fft + 1) + 192) * sizeof(float);
+  const size_t dec_smem = (size_t)(((n_taps + 4) & ~3) + 2 * ((kDecTile + (n_taps - 1) / 2 + 1 + 3) & ~3)) * sizeof(float);
+  if (resp_smem > 227 * 1024 || dec_smem > 227 * 1024) {
+    delete plan;
+    set_error("gtc_scqt_plan_create: n_fft %d x %d filters needs %zu B of shared memory (> 227 KB)", n_fft, filters_per_octave, resp_smem);
+    return GTC_E_UNSUP;
+  }
+  // h_filters [n_oct][2*fpo][n_fft] (row = filter*2 + {re,im}) -> device [n_oct][n_fft][groups*4]
+  const int n_real = 2 * filters_per_octave, g4 = p.groups * 4;
+  std::vector<float> tr((size_t)n_octaves * n_fft * g4, 0.f);
+  for (int i = 0; i < n_octaves; ++i)
+    for (int r = 0; r < n_real; ++r)
+      for (int n = 0; n < n_fft; ++n)
+        tr[((size_t)i * n_fft + n) * g4 + r] = h_filters[((size_t)i * n_real + r) * n_fft + n];
+  cudaError_t e = cudaMalloc((void**)&p.d_filters, tr.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(p.d_filters, tr.data(), tr.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p.d_taps, (size_t)n_taps * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(p.d_taps, h_taps, (size_t)n_taps * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(response_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resp_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(response_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resp_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(decimate2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(decimate2_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
+  if (e != cudaSuccess) {
+    set_error("gtc_scqt_plan_create: %s", cudaGetErrorString(e));
+    if (p.d_filters) cudaFree(p.d_filters);
+    if (p.d_taps) cudaFree(p.d_taps);
+    delete plan;
+    return GTC_E_CUDA;
+  }
+  *out = plan;
+  return GTC_OK;
+}
+
+extern "C" int gtc_scqt_plan_destroy(gtc_splan* plan) {
+  if (!plan) return GTC_OK;
+  if (plan->impl.d_filters) cudaFree(plan->impl.d_filters);
+  if (plan->impl.d_taps) cudaFree(plan->impl.d_taps);
+  delete plan;
+  return GTC_OK;
+}
+
+extern "C" int gtc_scqt_workspace_bytes(const gtc_splan* plan, int64_t n_seg, int64_t max_len, size_t* bytes) {
+  GTC_REQUIRE(plan && bytes && n_seg >= 0 && max_len >= 0 && max_len < 0x7fffffffLL, GTC_E_ARG, "gtc_scqt_workspace_bytes: bad argument");
+  *bytes = s_layout(plan->impl, n_seg, max_len).total;
+  return GTC_OK;
+}
+
+static int scqt_run(const gtc_splan* plan, const void* d_audio, int sample_format, const int64_t* d_seg_start,
+                    const int32_t* d_seg_valid, const int32_t* d_seg_len, int64_t n_seg, int64_t max_len, float* d_out,
+                    bool complex_out, void* d_workspace, size_t workspace_bytes, float power, float amin, float top_db,
+                    float cut_db, float floor_db, cudaStream_t st) {
+  GTC_REQUIRE(plan != nullptr, GTC_E_ARG, "gtc_scqt: plan is NULL");
+  GTC_REQUIRE(n_seg >= 0 && max_len >= 0 && max_len < 0x7fffffffLL, GTC_E_ARG, "gtc_scqt: sizes out of range");
+  GTC_REQUIRE(sample_format == GTC_SAMPLES_F32 || sample_format == GTC_SAMPLES_PCM16, GTC_E_ARG, "gtc_scqt: unknown sample format %d", sample_format);
+  if (n_seg == 0) return GTC_OK;
+  GTC_REQUIRE(d_audio && d_seg_start && d_seg_valid && d_seg_len && d_out && d_workspace, GTC_E_ARG, "gtc_scqt: null pointer");
+  const SPlanImpl& p = plan->impl;
+  int dev = -1;
+  GTC_CUDA_CHECK(cudaGetDevice(&dev));
+  GTC_REQUIRE(dev == p.device, GTC_E_ARG, "gtc_scqt: plan belongs to device %d, current device is %d", p.device, dev);
+  const SWorkspace w = s_layout(p, n_seg, max_len);
+  GTC_REQUIRE(workspace_bytes >= w.total, GTC_E_NOMEM, "gtc_scqt: workspace of %zu bytes, %zu needed", workspace_bytes, w.total);
+  GTC_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 15) == 0, GTC_E_ARG, "gtc_scqt: workspace must be 16-byte aligned");
+  char* ws = static_cast<char*>(d_workspace);
+  if (sample_format == GTC_SAMPLES_PCM16)
+    return run_structured(p, (const int16_t*)d_audio, d_seg_start, d_seg_valid, d_seg_len, n_seg, max_len, d_out, complex_out, ws, w,
+                          power, amin, top_db, cut_db, floor_db, st);
+  return run_structured(p, (const float*)d_audio, d_seg_start, d_seg_valid, d_seg_len, n_seg, max_len, d_out, complex_out, ws, w,
+                        power, amin, top_db, cut_db, floor_db, st);
+}
+
+extern "C" int gtc_scqt_segments_db(const gtc_splan* plan, const void* d_audio, int sample_format, const int64_t* d_seg_start,
+                                    const int32_t* d_seg_valid, const int32_t* d_seg_len, int64_t n_seg, int64_t max_len,
+                                    float* d_out_db, void* d_workspace, size_t workspace_bytes, float power, float amin,
+                                    float top_db, float cut_db, float floor_db, gtc_stream_t stream) {
+  GTC_REQUIRE(power > 0.f && amin > 0.f, GTC_E_ARG, "gtc_scqt_segments_db: power and amin must be positive");
+  return scqt_run(plan, d_audio, sample_format, d_seg_start, d_seg_valid, d_seg_len, n_seg, max_len, d_out_db, false, d_workspace,
+                  workspace_bytes, power, amin, top_db, cut_db, floor_db, (cudaStream_t)stream);
+}
+
+extern "C" int gtc_scqt_segments_complex(const gtc_splan* plan, const void* d_audio, int sample_format, const int64_t* d_seg_start,
+                                         const int32_t* d_seg_valid, const int32_t* d_seg_len, int64_t n_seg, int64_t max_len,
+                                         float* d_out_c, void* d_workspace, size_t workspace_bytes, gtc_stream_t stream) {
+  return scqt_run(plan, d_audio, sample_format, d_seg_start, d_seg_valid, d_seg_len, n_seg, max_len, d_out_c, true, d_workspace,
+                  workspace_bytes, 1.f, 1e-5f, 80.f, -60.f, -120.f, (cudaStream_t)stream);
+}

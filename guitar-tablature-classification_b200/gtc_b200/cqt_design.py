@@ -228,6 +228,51 @@ def build_operator(recipe: CqtRecipe, seg_len: int | None = None) -> np.ndarray:
     return np.ascontiguousarray(A.reshape(T * n_bins * 2, seg_len).astype(np.float32))
 
 
+def _recipe_grid(recipe: CqtRecipe):
+    """freqs, alpha, full-rate lengths of a recipe, with librosa.vqt's own argument checks."""
+    n_bins, bpo, n_oct = recipe.n_bins, recipe.bins_per_octave, recipe.n_octaves
+    sr = float(recipe.sr)
+    if recipe.hop_length % (2 ** (n_oct - 1)) != 0:
+        raise ValueError(f"hop_length must be a positive integer multiple of 2^{n_oct - 1} for {n_oct}-octave CQT")
+    freqs = recipe.fmin_hz * (2.0 ** (np.arange(n_bins, dtype=np.float64) / bpo))
+    alpha = _relative_bandwidth(freqs)
+    lengths = (recipe.filter_scale / alpha) * sr / freqs
+    cutoff = np.max(freqs * (1 + 0.5 * HANN_BANDWIDTH / (recipe.filter_scale / alpha)))
+    if cutoff > sr / 2:
+        raise ValueError(f"Wavelet basis with max frequency={freqs.max()} would exceed the Nyquist frequency={sr / 2}")
+    num_twos = (recipe.hop_length & -recipe.hop_length).bit_length() - 1
+    early = min(max(0, int(math.ceil(math.log2((sr / 2) / cutoff)) - 1) - 1), max(0, num_twos - n_oct + 1))
+    if early > 0:
+        raise NotImplementedError("recipes that trigger librosa's early down-sampling are not supported")
+    return freqs, alpha, lengths
+
+
+def structured_filters(recipe: CqtRecipe):
+    """Tables of the structured (multirate) evaluation, libgtc's gtc_scqt_plan_create inputs:
+    ``filters`` float32 [n_octaves, 2*filters_per_octave, n_fft] (row = filter*2 + {re, im}; octave 0 = top octave; every
+    scaling of librosa.vqt folded in: lengths/n_fft, sqrt(sr/octave_sr), 1/sqrt(full-rate length)), ``n_fft`` and the
+    2:1 decimator ``taps`` float32 with librosa.resample's sqrt(2) gain folded in.
+    Octaves whose own n_fft is smaller are zero-padded symmetrically, which leaves the centred frames unchanged."""
+    freqs, alpha, lengths = _recipe_grid(recipe)
+    n_bins, n_oct, sr = recipe.n_bins, recipe.n_octaves, float(recipe.sr)
+    n_filters = min(recipe.bins_per_octave, n_bins)
+    per_oct, octave_sr = [], sr
+    for i in range(n_oct):
+        hi = n_bins - n_filters * i
+        lo = max(0, hi - n_filters)
+        W, n_fft = octave_time_filters(freqs[lo:hi], alpha[lo:hi], octave_sr, sr, recipe.filter_scale, recipe.sparsity)
+        per_oct.append((W / np.sqrt(lengths[lo:hi])[:, None], n_fft))
+        octave_sr /= 2.0
+    n_fft_max = max(n for _, n in per_oct)
+    filters = np.zeros((n_oct, 2 * n_filters, n_fft_max), dtype=np.float32)
+    for i, (W, n_fft) in enumerate(per_oct):
+        pad = (n_fft_max - n_fft) // 2
+        filters[i, 0: 2 * len(W): 2, pad: pad + n_fft] = W.real
+        filters[i, 1: 2 * len(W): 2, pad: pad + n_fft] = W.imag
+    taps = (decimator_taps() * math.sqrt(2.0)).astype(np.float32)
+    return filters, n_fft_max, taps
+
+
 def _cache_dir() -> str:
     d = os.environ.get("GTC_CACHE_DIR", os.path.join(os.path.expanduser("~"), ".cache", "gtc_b200"))
     os.makedirs(d, exist_ok=True)

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .cqt_design import CqtRecipe, get_operator, n_frames_of
+from .cqt_design import CqtRecipe, get_operator, n_frames_of, structured_filters
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -143,6 +143,89 @@ class CqtPlan:
         _lib.check(_lib.load().gtc_cqt_segments_complex(self._h, _ptr(audio), _ptr(clip_off), _ptr(seg_off), n_clips, n_seg,
                                                         _ptr(out), _ptr(ws), ws.numel(), _stream()), "gtc_cqt_segments_complex")
         return torch.view_as_complex(out)
+
+
+class StructuredCqtPlan:
+    """Multirate evaluation of librosa.cqt for variable-length segments (decimation chain + per-octave filters),
+    the way librosa computes it.  Used where the collapsed operator of CqtPlan does not apply: the 3 s inference
+    segments of tablature_generator.py:616-620, whole clips, any sample rate."""
+
+    def __init__(self, recipe: CqtRecipe = CqtRecipe(), device: Optional[int] = None):
+        lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.GtcError("StructuredCqtPlan needs a CUDA device (there is no CPU fallback)")
+        self.recipe = recipe
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.n_bins, self.n_octaves, self.hop_length = recipe.n_bins, recipe.n_octaves, recipe.hop_length
+        filters, n_fft, taps = structured_filters(recipe)
+        self.n_fft = n_fft
+        filters = np.ascontiguousarray(filters, dtype=np.float32)
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.gtc_scqt_plan_create(C.byref(handle), self.device, self.n_octaves, n_fft, recipe.hop_length,
+                                                self.n_bins, filters.shape[1] // 2, filters.ctypes.data_as(C.c_void_p),
+                                                taps.ctypes.data_as(C.c_void_p), len(taps)), "gtc_scqt_plan_create")
+        self._h = handle
+        self._ws: Optional[torch.Tensor] = None
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _lib.load().gtc_scqt_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def frames(self, seg_len: int) -> int:
+        """librosa's frame count for a signal of ``seg_len`` samples (min over octaves of 1 + len_i // hop_i)."""
+        return int(_lib.load().gtc_scqt_frames(int(seg_len), self.hop_length, self.n_octaves))
+
+    def workspace(self, n_seg: int, max_len: int) -> torch.Tensor:
+        need = C.c_size_t()
+        _lib.check(_lib.load().gtc_scqt_workspace_bytes(self._h, n_seg, max_len, C.byref(need)), "gtc_scqt_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need.value:
+            self._ws = None
+            self._ws = torch.empty(max(need.value, 1024), dtype=torch.uint8, device=f"cuda:{self.device}")
+        return self._ws
+
+    def _run(self, audio, seg_start, seg_valid, seg_len, max_len, complex_out, out):
+        _need_cuda(audio, seg_start, seg_valid, seg_len)
+        assert audio.dtype in (torch.float32, torch.int16)
+        assert seg_start.dtype == torch.int64 and seg_valid.dtype == torch.int32 and seg_len.dtype == torch.int32
+        n_seg = seg_start.numel()
+        assert seg_valid.numel() == n_seg and seg_len.numel() == n_seg
+        t_max = self.frames(max_len)
+        shape = (n_seg, self.n_bins, t_max, 2) if complex_out else (n_seg, self.n_bins, t_max)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=audio.device)
+        assert out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == shape
+        ws = self.workspace(n_seg, max_len)
+        fmt = _lib.GTC_SAMPLES_PCM16 if audio.dtype == torch.int16 else _lib.GTC_SAMPLES_F32
+        r = self.recipe
+        if complex_out:
+            _lib.check(_lib.load().gtc_scqt_segments_complex(self._h, _ptr(audio), fmt, _ptr(seg_start), _ptr(seg_valid), _ptr(seg_len),
+                                                             n_seg, max_len, _ptr(out), _ptr(ws), ws.numel(), _stream()),
+                       "gtc_scqt_segments_complex")
+            return torch.view_as_complex(out)
+        _lib.check(_lib.load().gtc_scqt_segments_db(self._h, _ptr(audio), fmt, _ptr(seg_start), _ptr(seg_valid), _ptr(seg_len), n_seg,
+                                                    max_len, _ptr(out), _ptr(ws), ws.numel(), r.power, r.amin, r.top_db, r.cut_db,
+                                                    r.floor_db, _stream()), "gtc_scqt_segments_db")
+        return out
+
+    def segments_db(self, audio: torch.Tensor, seg_start: torch.Tensor, seg_valid: torch.Tensor, seg_len: torch.Tensor,
+                    max_len: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """audio: device fp32 (or int16 PCM) samples; segment s = audio[seg_start[s] : +seg_valid[s]] zero-padded to
+        seg_len[s] samples.  Returns dB features [n_seg, n_bins, frames(max_len)] (recipe's power/amin/top_db/cut)."""
+        return self._run(audio, seg_start, seg_valid, seg_len, int(max_len), False, out)
+
+    def segments_complex(self, audio: torch.Tensor, seg_start: torch.Tensor, seg_valid: torch.Tensor, seg_len: torch.Tensor,
+                         max_len: int) -> torch.Tensor:
+        """[n_seg, n_bins, frames(max_len)] complex64 (== librosa.cqt of every segment)."""
+        return self._run(audio, seg_start, seg_valid, seg_len, int(max_len), True, None)
 
 
 def set_option(option: int, value: int) -> None:

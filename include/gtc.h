@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GTC_VERSION 100
+#define GTC_VERSION 101
 
 #define GTC_OK          0
 #define GTC_E_ARG      -1   /* invalid argument                      */
@@ -107,6 +107,38 @@ int gtc_set_option(int option, int value);
 int gtc_cqt_segments_complex(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off,
                              const int64_t* d_seg_off, int64_t n_clips, int64_t n_seg, float* d_out_c,
                              void* d_workspace, size_t workspace_bytes, gtc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Structured (multirate) CQT of variable-length segments -- replaces librosa.cqt + np.abs + amplitude_to_db where the
+ * collapsed segment operator does not apply: the inference front-end of /root/reference/tablature_generator.py:616-620
+ * (sr 22 050, hop 512, fmin C2, 84 bins, ref=np.max, 3 s segments cut by segment_audio :637-666), whole-clip CQTs and
+ * any sample rate.  Evaluated the way librosa does: a chain of soxr-HQ 2:1 decimations (shared-memory FIR) and, per
+ * octave, the wavelet filters applied to centred zero-padded frames.
+ *
+ * h_filters [n_octaves][2*filters_per_octave][n_fft] fp32: time-domain filters of octave i (0 = top octave),
+ *           row = filter*2 + {re, im}, all scalings folded in (gtc_b200.cqt_design.structured_filters).
+ * h_taps    [n_taps] fp32: the 2:1 decimator with librosa's sqrt(2) gain folded in; n_taps == 1 (mod 4).
+ * Segment s is the signal  x[j] = audio[d_seg_start[s] + j] for j < d_seg_valid[s], 0 for d_seg_valid[s] <= j < d_seg_len[s]
+ * (np.pad of the tail, tablature_generator.py:658-660); its frame count is gtc_scqt_frames(d_seg_len[s], hop, n_octaves).
+ * Outputs are [n_seg, n_bins, t_max] with t_max = gtc_scqt_frames(max_len, ...), frames past a segment's own count hold
+ * the value of an all-zero frame; max_len >= every d_seg_len[s].
+ * ------------------------------------------------------------------------------------------------------------ */
+#define GTC_SAMPLES_F32    0
+#define GTC_SAMPLES_PCM16  1   /* int16 PCM, converted x/32768 on the device (== librosa.load of a PCM_16 file) */
+typedef struct gtc_splan gtc_splan;
+int gtc_scqt_frames(int64_t seg_len, int hop_length, int n_octaves);
+int gtc_scqt_plan_create(gtc_splan** out, int device, int n_octaves, int n_fft, int hop_length, int n_bins,
+                         int filters_per_octave, const float* h_filters, const float* h_taps, int n_taps);
+int gtc_scqt_plan_destroy(gtc_splan* plan);
+int gtc_scqt_workspace_bytes(const gtc_splan* plan, int64_t n_seg, int64_t max_len, size_t* bytes);
+int gtc_scqt_segments_db(const gtc_splan* plan, const void* d_audio, int sample_format, const int64_t* d_seg_start,
+                         const int32_t* d_seg_valid, const int32_t* d_seg_len, int64_t n_seg, int64_t max_len,
+                         float* d_out_db, void* d_workspace, size_t workspace_bytes,
+                         float power, float amin, float top_db, float cut_db, float floor_db, gtc_stream_t stream);
+/* d_out_c [n_seg, n_bins, t_max, 2] fp32 (== librosa.cqt of every segment) */
+int gtc_scqt_segments_complex(const gtc_splan* plan, const void* d_audio, int sample_format, const int64_t* d_seg_start,
+                              const int32_t* d_seg_valid, const int32_t* d_seg_len, int64_t n_seg, int64_t max_len,
+                              float* d_out_c, void* d_workspace, size_t workspace_bytes, gtc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Label rasterisation -- replaces GuitarTablatureExtractor.extract_tablature_from_jams + midi_to_tablature +

@@ -15,7 +15,8 @@ def declared_symbols():
 def test_header_declares_expected_entry_points():
     syms = declared_symbols()
     for name in ("gtc_cqt_plan_create", "gtc_cqt_segments_db", "gtc_rasterize_tabs", "gtc_patches",
-                 "gtc_labels_argmax", "gtc_labels_vit_heads", "gtc_last_error", "gtc_version"):
+                 "gtc_labels_argmax", "gtc_labels_vit_heads", "gtc_last_error", "gtc_version",
+                 "gtc_scqt_plan_create", "gtc_scqt_segments_db", "gtc_scqt_segments_complex"):
         assert name in syms
 
 
@@ -25,7 +26,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in syms:
         assert hasattr(lib, name), f"libgtc.so does not export {name}"
     assert sorted(_lib.PROTOTYPES) == syms, "ctypes prototypes and include/gtc.h disagree"
-    assert lib.gtc_version() == 100
+    assert lib.gtc_version() == 101
 
 
 def test_no_torch_types_in_abi():

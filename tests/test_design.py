@@ -34,3 +34,45 @@ def test_operator_reproduces_oracle_cqt(basis_cache):
 def test_non_power_hop_is_rejected():
     with pytest.raises(ValueError):
         cd.build_operator(cd.CqtRecipe(hop_length=1000))
+
+
+def emulate_structured(y, filters, n_fft, taps, hop, n_bins):
+    """What libgtc's structured kernels compute (csrc/cqt_structured.cu), in float64 NumPy from the float32 tables."""
+    n_oct, n_real, _ = filters.shape
+    nf = n_real // 2
+    c = (len(taps) - 1) // 2
+    resp, x, frames = [], y.astype(np.float64), []
+    for i in range(n_oct):
+        T = 1 + len(x) // hop
+        frames.append(T)
+        xp = np.concatenate([np.zeros(n_fft // 2), x, np.zeros(n_fft // 2 + hop)])
+        F = np.stack([xp[t * hop: t * hop + n_fft] for t in range(T)])            # (T, n_fft)
+        R = F @ filters[i].astype(np.float64).T                                   # (T, 2*nf)
+        resp.append((R[:, 0::2] + 1j * R[:, 1::2]).T)                             # (nf, T)
+        if hop % 2 == 0:
+            full = np.convolve(x, taps.astype(np.float64))
+            x = full[c: c + 2 * ((len(x) + 1) // 2): 2]
+            hop //= 2
+    T = min(frames)
+    V = np.zeros((n_bins, T), dtype=np.complex128)
+    for i, Ri in enumerate(resp):
+        hi = n_bins - nf * i
+        lo = max(0, hi - nf)
+        V[lo:hi] = Ri[: hi - lo, :T]
+    return V
+
+
+@pytest.mark.parametrize("kw,n", [
+    (dict(), 4410),                                                               # cqt.py:55 at 22.05 kHz
+    (dict(sr=44100.0), 8820),                                                     # GuitarSet native rate, n_fft 256
+    (dict(hop_length=512, n_bins=84, fmin=65.40639132514966), 22050),             # tablature_generator.py:616-617
+    (dict(n_bins=90), 5000),                                                      # partial lowest octave
+])
+def test_structured_tables_reproduce_oracle_cqt(kw, n):
+    r = cd.CqtRecipe(**kw)
+    filters, n_fft, taps = cd.structured_filters(r)
+    x = make_test_audio(n, seed=3, sr=r.sr)
+    C = co.cqt(x, sr=r.sr, hop_length=r.hop_length, fmin=r.fmin_hz, n_bins=r.n_bins)
+    V = emulate_structured(x, filters, n_fft, taps, r.hop_length, r.n_bins)
+    assert V.shape == C.shape
+    assert np.abs(V - C).max() < 3e-6 * np.abs(C).max()
