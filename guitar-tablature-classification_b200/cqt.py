@@ -18,7 +18,7 @@ from gtc_b200 import audio_io, features
 from gtc_b200.cqt_design import CqtRecipe
 
 
-def process_all_audio(dataset_path, window_size=0.2, hop_size=0.1, save_path='output', files_per_batch=64):
+def process_all_audio(dataset_path, window_size=0.2, hop_size=0.1, save_path='output', files_per_batch=64, packed=False):
     os.makedirs(save_path, exist_ok=True)
     audio_files = [f for f in os.listdir(dataset_path) if f.endswith('.wav')]
     written = 0
@@ -39,8 +39,11 @@ def process_all_audio(dataset_path, window_size=0.2, hop_size=0.1, save_path='ou
             for (name, y), f in zip(group, feats):
                 print(f'Processing {len(f)} valid segments for: {name}')
                 base_name = os.path.splitext(name)[0]
-                for k in range(len(f)):
-                    audio_io.save_feature(os.path.join(save_path, f"{base_name}_segment_{k}.npy"), f[k])
+                if packed:      # one file per clip instead of ~10 per second of audio; audio_io.explode_features undoes it
+                    audio_io.save_features_packed(os.path.join(save_path, base_name + audio_io.FEATURE_PACK_SUFFIX), f)
+                else:
+                    for k in range(len(f)):
+                        audio_io.save_feature(os.path.join(save_path, f"{base_name}_segment_{k}.npy"), f[k])
                 written += len(f)
                 print(f'Saved {len(f)} valid segments for {name} in {save_path}')
     return written

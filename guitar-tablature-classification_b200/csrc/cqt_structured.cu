@@ -67,7 +67,7 @@ template <typename In>
 __global__ void __launch_bounds__(256)
 decimate2_kernel(const In* __restrict__ src, const int64_t* __restrict__ seg_start, const int32_t* __restrict__ seg_valid,
                  const int32_t* __restrict__ seg_len, int stage, int64_t src_stride, float* __restrict__ dst,
-                 int64_t dst_stride, const float* __restrict__ taps, int n_taps, int tiles) {
+                 int64_t dst_stride, const float* __restrict__ taps, int n_taps, int tiles, float gain) {
   extern __shared__ float sm[];
   const int c = (n_taps - 1) >> 1;                 // even: n_taps == 1 (mod 4)
   const int span = kDecTile + c + 1;
@@ -116,7 +116,7 @@ decimate2_kernel(const In* __restrict__ src, const int64_t* __restrict__ seg_sta
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int k = k0 + u0 + r * 256;
-    if (k < len_out) y[k] = acc[r];
+    if (k < len_out) y[k] = acc[r] * gain;
   }
 }
 
@@ -295,11 +295,11 @@ static int run_structured(const SPlanImpl& p, const In* d_audio, const int64_t* 
     float* dst = wsf + w.bufs.off[i + 1];
     if (i == 0)
       decimate2_kernel<In><<<(unsigned)blocks, 256, dec_smem, st>>>(d_audio, d_seg_start, d_seg_valid, d_seg_len, 0, 0, dst,
-                                                                     w.bufs.stride[1], p.d_taps, p.n_taps, tiles);
+                                                                     w.bufs.stride[1], p.d_taps, p.n_taps, tiles, 1.f);
     else
       decimate2_kernel<float><<<(unsigned)blocks, 256, dec_smem, st>>>(wsf + w.bufs.off[i], nullptr, d_seg_valid, d_seg_len, i,
                                                                         w.bufs.stride[i], dst, w.bufs.stride[i + 1], p.d_taps,
-                                                                        p.n_taps, tiles);
+                                                                        p.n_taps, tiles, 1.f);
     GTC_CUDA_CHECK(cudaGetLastError());
     len = out_len;
   }
@@ -457,4 +457,33 @@ extern "C" int gtc_scqt_segments_complex(const gtc_splan* plan, const void* d_au
                                          float* d_out_c, void* d_workspace, size_t workspace_bytes, gtc_stream_t stream) {
   return scqt_run(plan, d_audio, sample_format, d_seg_start, d_seg_valid, d_seg_len, n_seg, max_len, d_out_c, true, d_workspace,
                   workspace_bytes, 1.f, 1e-5f, 80.f, -60.f, -120.f, (cudaStream_t)stream);
+}
+
+// One 2:1 soxr-HQ stage on its own: librosa.load(path, sr=native/2) / librosa.resample(orig_sr=2k, target_sr=k,
+// res_type='soxr_hq') as called at /root/reference/tablature_generator.py:613,650 for 44.1 kHz files (scale=False there,
+// so `gain` = 1/sqrt(2) undoes the sqrt(2) folded into the plan's taps; gain = 1 gives the CQT's own scale=True stage).
+extern "C" int gtc_scqt_decimate(const gtc_splan* plan, const void* d_audio, int sample_format, const int64_t* d_seg_start,
+                                 const int32_t* d_seg_valid, const int32_t* d_seg_len, int64_t n_seg, int64_t max_len,
+                                 float* d_out, int64_t out_stride, float gain, gtc_stream_t stream) {
+  GTC_REQUIRE(plan != nullptr, GTC_E_ARG, "gtc_scqt_decimate: plan is NULL");
+  GTC_REQUIRE(n_seg >= 0 && max_len >= 0 && max_len < 0x7fffffffLL, GTC_E_ARG, "gtc_scqt_decimate: sizes out of range");
+  GTC_REQUIRE(sample_format == GTC_SAMPLES_F32 || sample_format == GTC_SAMPLES_PCM16, GTC_E_ARG, "gtc_scqt_decimate: unknown sample format %d", sample_format);
+  if (n_seg == 0 || max_len == 0) return GTC_OK;
+  GTC_REQUIRE(d_audio && d_seg_start && d_seg_valid && d_seg_len && d_out, GTC_E_ARG, "gtc_scqt_decimate: null pointer");
+  GTC_REQUIRE(out_stride >= (max_len + 1) / 2, GTC_E_ARG, "gtc_scqt_decimate: out_stride smaller than ceil(max_len/2)");
+  const SPlanImpl& p = plan->impl;
+  const int c = (p.n_taps - 1) / 2;
+  const size_t dec_smem = (size_t)(((p.n_taps + 4) & ~3) + 2 * ((kDecTile + c + 1 + 3) & ~3)) * sizeof(float);
+  const int tiles = (int)ceil_div((max_len + 1) / 2, kDecTile);
+  const int64_t blocks = n_seg * tiles;
+  GTC_REQUIRE(blocks < 0x7fffffffLL, GTC_E_ARG, "gtc_scqt_decimate: too many tiles; split the batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sample_format == GTC_SAMPLES_PCM16)
+    decimate2_kernel<int16_t><<<(unsigned)blocks, 256, dec_smem, st>>>((const int16_t*)d_audio, d_seg_start, d_seg_valid, d_seg_len, 0, 0,
+                                                                        d_out, out_stride, p.d_taps, p.n_taps, tiles, gain);
+  else
+    decimate2_kernel<float><<<(unsigned)blocks, 256, dec_smem, st>>>((const float*)d_audio, d_seg_start, d_seg_valid, d_seg_len, 0, 0,
+                                                                      d_out, out_stride, p.d_taps, p.n_taps, tiles, gain);
+  GTC_CUDA_CHECK(cudaGetLastError());
+  return GTC_OK;
 }

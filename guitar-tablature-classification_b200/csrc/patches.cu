@@ -22,6 +22,7 @@ struct PatchParams {
   int64_t n;
   int h_in, t_in, oh, ow;
   int mode;
+  int prenorm;          // input is already (x+120)/120 clipped (tablature-generator (1).py:334-335): skip normalise_db
   int parts;            // row blocks per segment
   int rows_per_part;
   unsigned int* ticket; // zeroed before the launch
@@ -56,8 +57,8 @@ __device__ __forceinline__ void axis_taps(int d, int n_in, int n_out, int mode, 
   }
 }
 
-__device__ __forceinline__ float normalise_db(float x) {           // ViT_dataloader.py:31-32
-  return fminf(fmaxf((x + 120.f) / 120.f, 0.f), 1.f);
+__device__ __forceinline__ float normalise_db(float x, int prenorm = 0) {           // ViT_dataloader.py:31-32
+  return prenorm ? x : fminf(fmaxf((x + 120.f) / 120.f, 0.f), 1.f);
 }
 
 constexpr int kPatchThreads = 224;
@@ -148,14 +149,14 @@ patch_kernel(const PatchParams p) {
         const int o = tid + k * blockDim.x;
         if (k < n_pre && o < n_src) {
           const int r = o / t_in, c = o - r * t_in;
-          s_src[(flip ? (h_in - 1 - r) : r) * t_in + c] = normalise_db(pre[k]);
+          s_src[(flip ? (h_in - 1 - r) : r) * t_in + c] = normalise_db(pre[k], p.prenorm);
         }
       }
     } else {
       const int64_t s = p.index ? p.index[seg] : seg;
       for (int o = tid; o < n_src; o += blockDim.x) {
         const int r = o / t_in, c = o - r * t_in;
-        s_src[(flip ? (h_in - 1 - r) : r) * t_in + c] = normalise_db(__ldg(p.db + s * n_src + o));
+        s_src[(flip ? (h_in - 1 - r) : r) * t_in + c] = normalise_db(__ldg(p.db + s * n_src + o), p.prenorm);
       }
     }
     if (tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
@@ -234,7 +235,9 @@ extern "C" int gtc_patches(const float* d_db, const int64_t* d_index, int64_t n,
   GTC_REQUIRE(n >= 0, GTC_E_ARG, "gtc_patches: negative n");
   if (n == 0) return GTC_OK;
   GTC_REQUIRE(d_db && d_out, GTC_E_ARG, "gtc_patches: null pointer");
-  GTC_REQUIRE(mode == GTC_PATCH_VIT || mode == GTC_PATCH_CNN, GTC_E_ARG, "gtc_patches: unknown mode %d", mode);
+  GTC_REQUIRE(mode == GTC_PATCH_VIT || mode == GTC_PATCH_CNN || mode == GTC_PATCH_VIT_PRENORM, GTC_E_ARG, "gtc_patches: unknown mode %d", mode);
+  const int prenorm = mode == GTC_PATCH_VIT_PRENORM;
+  if (prenorm) mode = GTC_PATCH_VIT;
   GTC_REQUIRE(n_bins > 0 && n_frames > 0 && out_h > 0 && out_w > 0, GTC_E_ARG, "gtc_patches: non-positive size");
   GTC_REQUIRE((int64_t)n_bins * n_frames <= kMaxSrc, GTC_E_UNSUP, "gtc_patches: n_bins*n_frames > %d", kMaxSrc);
   GTC_REQUIRE(out_h <= 2048 && out_w <= 4096, GTC_E_UNSUP, "gtc_patches: output larger than 2048x4096");
@@ -262,7 +265,7 @@ extern "C" int gtc_patches(const float* d_db, const int64_t* d_index, int64_t n,
   unsigned int* ticket = ticket_base[dev] + (__atomic_fetch_add(&next_slot, 1u, __ATOMIC_RELAXED) % kTicketSlots);
   GTC_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
 
-  PatchParams p{d_db, d_index, n, n_bins, n_frames, out_h, out_w, mode, parts, rpp, ticket, d_out};
+  PatchParams p{d_db, d_index, n, n_bins, n_frames, out_h, out_w, mode, prenorm, parts, rpp, ticket, d_out};
   const int tp = (n_frames + 3) & ~3;
   const size_t smem = sizeof(float) * (((size_t)n_bins * n_frames + 3) / 4 * 4 + (size_t)rpp * tp + (size_t)out_h * 8);
   GTC_REQUIRE(smem <= 200 * 1024, GTC_E_UNSUP, "gtc_patches: %zu bytes of shared memory needed", smem);

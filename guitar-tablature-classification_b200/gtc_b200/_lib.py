@@ -19,8 +19,10 @@ GTC_OPT_GEMM_MAX_CTAS = 2
 GTC_OPT_PATCH_MAX_CTAS = 16
 GTC_PATCH_VIT = 0
 GTC_PATCH_CNN = 1
+GTC_PATCH_VIT_PRENORM = 2
 GTC_SAMPLES_F32 = 0
 GTC_SAMPLES_PCM16 = 1
+GTC_AUG_TIME_SHIFT, GTC_AUG_NOISE, GTC_AUG_FREQ_MASK, GTC_AUG_TIME_MASK = 1, 2, 3, 4
 
 # every symbol include/gtc.h declares: name -> (restype, argtypes)
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
@@ -43,11 +45,14 @@ PROTOTYPES = {
     "gtc_scqt_plan_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, _vp, _i]),
     "gtc_scqt_plan_destroy": (_i, [_vp]),
     "gtc_scqt_workspace_bytes": (_i, [_vp, _i64, _i64, C.POINTER(_sz)]),
+    "gtc_scqt_decimate": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _f, _vp]),
     "gtc_scqt_segments_db": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp]),
     "gtc_scqt_segments_complex": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "gtc_rasterize_tabs": (_i, [_vp] * 11 + [_i64, _i64, _vp, _vp, _vp]),
     "gtc_labels_argmax": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "gtc_labels_vit_heads": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "gtc_augment_batch": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f, C.c_uint64, _i, _f, _vp]),
+    "gtc_db_normalize": (_i, [_vp, _i64, _f, _vp, _vp]),
     "gtc_patches": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 

@@ -6,6 +6,10 @@
 * ``save_feature``        writes what ``np.save(path, new_CQT)`` writes at cqt.py:63: '<f4', shape (n_bins, T),
   Fortran order (librosa's __trim_stack allocates order="F" and every later op preserves it).
 * ``save_label``          writes the (6, 19) '|i1' C-order file of jam_to_tablature.py:323-324 (242 bytes).
+* packed files            one ``.npy`` per clip holding all its segments ([n_seg, n_bins, T] '<f4' or [n_seg, 6, 19] '|i1')
+  instead of ~10 files per second of audio; ``explode_features`` / ``explode_labels`` turn a
+  packed file back into exactly the per-segment files the reference writes, ``packed_item_names`` gives the names those
+  files would have so that loaders keep the reference's sorted-listdir pairing order.
 """
 from __future__ import annotations
 
@@ -65,3 +69,62 @@ def save_feature(path, feat: np.ndarray) -> None:
 
 def save_label(path, tab: np.ndarray) -> None:
     np.save(path, np.ascontiguousarray(tab, dtype=np.int8))
+
+
+# ---------------------------------------------------------------------------------------------------- packed files
+
+FEATURE_PACK_SUFFIX = "_segments.npy"      # {base}_segments.npy       <->  {base}_segment_{k}.npy      (cqt.py:62)
+LABEL_PACK_SUFFIX = "_tabs.npy"            # {base}_tabs.npy           <->  {base}/{base}_{i:04d}.npy   (jam_to_tablature.py:323)
+
+
+def save_features_packed(path, feats: np.ndarray) -> None:
+    """[n_seg, n_bins, T] float32, C order: item k is the array cqt.py:63 would save as segment k."""
+    feats = np.ascontiguousarray(feats, dtype=np.float32)
+    assert feats.ndim == 3
+    np.save(path, feats)
+
+
+def save_labels_packed(path, tabs: np.ndarray, indices=None) -> None:
+    """[n, 6, 19] int8; ``indices`` (the segment numbers kept, jam_to_tablature.py:303-309) travel in a side file."""
+    tabs = np.ascontiguousarray(tabs, dtype=np.int8)
+    assert tabs.ndim == 3 and tabs.shape[1:] == (6, 19)
+    np.save(path, tabs)
+    if indices is not None:
+        np.save(str(path)[: -len(".npy")] + ".idx.npy", np.asarray(indices, dtype=np.int64))
+
+
+def packed_item_names(packed_name: str, n: int, indices=None):
+    """File names the reference would have written for the items of a packed file."""
+    import os
+    name = os.path.basename(str(packed_name))
+    if name.endswith(FEATURE_PACK_SUFFIX):
+        base = name[: -len(FEATURE_PACK_SUFFIX)]
+        return [f"{base}_segment_{k}.npy" for k in range(n)]
+    if name.endswith(LABEL_PACK_SUFFIX):
+        base = name[: -len(LABEL_PACK_SUFFIX)]
+        idx = range(n) if indices is None else indices
+        return [f"{base}_{int(i):04d}.npy" for i in idx]
+    raise ValueError(f"{packed_name} is not a packed feature/label file")
+
+
+def explode_features(packed_path, out_dir) -> int:
+    """Write the reference's per-segment feature files (Fortran order, cqt.py:62-63) from a packed file."""
+    import os
+    arr = np.load(packed_path)
+    os.makedirs(out_dir, exist_ok=True)
+    for name, a in zip(packed_item_names(packed_path, len(arr)), arr):
+        save_feature(os.path.join(out_dir, name), a)
+    return len(arr)
+
+
+def explode_labels(packed_path, out_dir) -> int:
+    """Write {out_dir}/{base}/{base}_{i:04d}.npy (jam_to_tablature.py:280,323-324) from a packed label file."""
+    import os
+    arr = np.load(packed_path)
+    idx_path = str(packed_path)[: -len(".npy")] + ".idx.npy"
+    idx = np.load(idx_path) if os.path.exists(idx_path) else None
+    base = os.path.basename(str(packed_path))[: -len(LABEL_PACK_SUFFIX)]
+    os.makedirs(os.path.join(out_dir, base), exist_ok=True)
+    for name, a in zip(packed_item_names(packed_path, len(arr), idx), arr):
+        save_label(os.path.join(out_dir, base, name), a)
+    return len(arr)

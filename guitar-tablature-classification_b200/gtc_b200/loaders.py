@@ -24,18 +24,37 @@ def _device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _load_dir(directory: str, suffix: str):
+    """(names, arrays) in the order sorted(os.listdir) gives the reference (my_dataloader.py:10-11 / ViT_dataloader.py:10-11).
+    Packed per-clip files (audio_io.save_*_packed) are expanded into the items -- and the names -- the reference's
+    per-segment files would have had, so the pairing by sorted position is unchanged."""
+    from . import audio_io
+    items = []
+    for f in os.listdir(directory):
+        if not f.endswith(suffix) or f.endswith(".idx.npy"):
+            continue
+        a = np.load(os.path.join(directory, f))
+        if a.ndim == 3 and (f.endswith(audio_io.FEATURE_PACK_SUFFIX) or f.endswith(audio_io.LABEL_PACK_SUFFIX)):
+            idx_path = os.path.join(directory, f[: -len(".npy")] + ".idx.npy")
+            idx = np.load(idx_path) if os.path.exists(idx_path) else None
+            items.extend(zip(audio_io.packed_item_names(f, len(a), idx), a))
+        else:
+            items.append((f, a))
+    items.sort(key=lambda it: it[0])
+    return [n for n, _ in items], [a for _, a in items]
+
+
 def load_feature_dir(audio_dir: str, suffix: str = ".npy"):
     """sorted(listdir) order, as my_dataloader.py:10 / ViT_dataloader.py:10.  Returns (names, [N, n_bins, T] fp32)."""
-    names = sorted(f for f in os.listdir(audio_dir) if f.endswith(suffix))
-    arrs = [np.load(os.path.join(audio_dir, f)).astype(np.float32) for f in names]
+    names, arrs = _load_dir(audio_dir, suffix)
+    arrs = [a.astype(np.float32) for a in arrs]
     if arrs and any(a.shape != arrs[0].shape for a in arrs):
         raise ValueError("feature files of one dataset must share a shape (n_bins, T)")
     return names, (np.stack(arrs) if arrs else np.zeros((0, 96, 5), np.float32))
 
 
 def load_label_dir(annotation_dir: str):
-    names = sorted(f for f in os.listdir(annotation_dir) if f.endswith('.npy'))
-    arrs = [np.load(os.path.join(annotation_dir, f)) for f in names]
+    names, arrs = _load_dir(annotation_dir, ".npy")
     for f, a in zip(names, arrs):
         if a.shape != (6, 19):
             print(f"Warning: Annotation has unexpected shape: {a.shape} ({f})")

@@ -216,6 +216,22 @@ class StructuredCqtPlan:
                                                     r.floor_db, _stream()), "gtc_scqt_segments_db")
         return out
 
+    def halve_rate(self, audio: torch.Tensor, scale: bool = False) -> torch.Tensor:
+        """librosa.resample(y, orig_sr=2k, target_sr=k, res_type='soxr_hq', scale=scale) of one device signal
+        (what librosa.load(path, sr=native/2) applies, tablature_generator.py:613,650): fp32 [ceil(n/2)]."""
+        _need_cuda(audio)
+        assert audio.dim() == 1 and audio.dtype in (torch.float32, torch.int16)
+        n = audio.numel()
+        out = torch.empty((n + 1) // 2, dtype=torch.float32, device=audio.device)
+        if n == 0:
+            return out
+        st = torch.zeros(1, dtype=torch.int64, device=audio.device)
+        ln = torch.full((1,), n, dtype=torch.int32, device=audio.device)
+        fmt = _lib.GTC_SAMPLES_PCM16 if audio.dtype == torch.int16 else _lib.GTC_SAMPLES_F32
+        _lib.check(_lib.load().gtc_scqt_decimate(self._h, _ptr(audio), fmt, _ptr(st), _ptr(ln), _ptr(ln), 1, n, _ptr(out),
+                                                 out.numel(), 1.0 if scale else 0.7071067811865476, _stream()), "gtc_scqt_decimate")
+        return out
+
     def segments_db(self, audio: torch.Tensor, seg_start: torch.Tensor, seg_valid: torch.Tensor, seg_len: torch.Tensor,
                     max_len: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """audio: device fp32 (or int16 PCM) samples; segment s = audio[seg_start[s] : +seg_valid[s]] zero-padded to

@@ -55,7 +55,8 @@ def _rasterize(note_sets, contour_sets, times_per_clip):
 
 
 class GuitarTablatureExtractor:
-    def __init__(self, jams_dir, audio_dir, cqt_images_dir, output_dir):
+    def __init__(self, jams_dir, audio_dir, cqt_images_dir, output_dir, packed=False):
+        self.packed = bool(packed)          # True: one {base}_tabs.npy per clip instead of one file per segment
         self.jams_dir = Path(jams_dir)
         self.audio_dir = Path(audio_dir)
         self.cqt_images_dir = Path(cqt_images_dir)
@@ -154,11 +155,15 @@ class GuitarTablatureExtractor:
         tabs, _, soff = _rasterize([j["notes"] for j in jobs], [j["contour"] for j in jobs], [j["times"] for j in jobs])
         for c, j in enumerate(jobs):
             out_dir = self.output_dir / j["base"]
-            out_dir.mkdir(exist_ok=True)
+            if not getattr(self, "packed", False):
+                out_dir.mkdir(exist_ok=True)
             mine = tabs[soff[c]:soff[c + 1]]
             stats = {'total': 0, 'with_notes': 0, 'with_first_string': 0}
+            if getattr(self, "packed", False):       # one file per clip; audio_io.explode_labels restores the reference's tree
+                audio_io.save_labels_packed(self.output_dir / (j["base"] + audio_io.LABEL_PACK_SUFFIX), mine, j["keep"])
             for i, tab in zip(j["keep"], mine):
-                audio_io.save_label(out_dir / f"{j['base']}_{int(i):04d}.npy", tab)
+                if not getattr(self, "packed", False):
+                    audio_io.save_label(out_dir / f"{j['base']}_{int(i):04d}.npy", tab)
                 stats['total'] += 1
                 stats['with_notes'] += int(tab.sum() > 0)
                 stats['with_first_string'] += int(tab[0].sum() > 0)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GTC_VERSION 101
+#define GTC_VERSION 102
 
 #define GTC_OK          0
 #define GTC_E_ARG      -1   /* invalid argument                      */
@@ -44,6 +44,7 @@ extern "C" {
 /* patch modes */
 #define GTC_PATCH_VIT  0   /* ViT_dataloader.py:31-51  : (x+120)/120, clip, bicubic, 3 identical channels            */
 #define GTC_PATCH_CNN  1   /* my_dataloader.py:17-21   : grey picture (top row = highest bin), bilinear, ImageNet normalise */
+#define GTC_PATCH_VIT_PRENORM 2 /* "tablature-generator (1).py":349-368 prepare_for_vit: input already normalised to [0,1]; bicubic, 3 channels */
 
 typedef struct gtc_plan gtc_plan;
 typedef void* gtc_stream_t;
@@ -135,6 +136,12 @@ int gtc_scqt_segments_db(const gtc_splan* plan, const void* d_audio, int sample_
                          const int32_t* d_seg_valid, const int32_t* d_seg_len, int64_t n_seg, int64_t max_len,
                          float* d_out_db, void* d_workspace, size_t workspace_bytes,
                          float power, float amin, float top_db, float cut_db, float floor_db, gtc_stream_t stream);
+/* One 2:1 stage on its own: d_out[s][k], k < ceil(d_seg_len[s]/2), row stride out_stride floats.  gain = 1 is the CQT's
+ * stage (librosa.resample scale=True); gain = 1/sqrt(2) is librosa.load(path, sr=native/2) -- tablature_generator.py:613,650
+ * on a 44.1 kHz file. */
+int gtc_scqt_decimate(const gtc_splan* plan, const void* d_audio, int sample_format, const int64_t* d_seg_start,
+                      const int32_t* d_seg_valid, const int32_t* d_seg_len, int64_t n_seg, int64_t max_len,
+                      float* d_out, int64_t out_stride, float gain, gtc_stream_t stream);
 /* d_out_c [n_seg, n_bins, t_max, 2] fp32 (== librosa.cqt of every segment) */
 int gtc_scqt_segments_complex(const gtc_splan* plan, const void* d_audio, int sample_format, const int64_t* d_seg_start,
                               const int32_t* d_seg_valid, const int32_t* d_seg_len, int64_t n_seg, int64_t max_len,
@@ -173,6 +180,31 @@ int gtc_labels_vit_heads(const int8_t* d_tabs, const int64_t* d_index, int64_t n
  * ------------------------------------------------------------------------------------------------------------ */
 int gtc_patches(const float* d_db, const int64_t* d_index, int64_t n, int n_bins, int n_frames,
                 int out_h, int out_w, int mode, float* d_out, gtc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Batch augmentation and dB normalisation -- replaces the torch op chains of /root/reference/ViT_engine.py:28-117
+ * (time_shift :28-42, add_noise :44-47, frequency_mask :49-63, time_mask :65-79, composed by augment_batch :81-93,
+ * then db_normalize :112-117) with one read + one write of the batch.
+ * d_in/d_out [batch, channels, dim2, dim3] fp32 (dim3 % 4 == 0).  h_ops[n_ops]: DIFFERENT GTC_AUG_* ops in the order
+ * the reference would apply them (host array).  Parameters are the values the reference draws with `random`:
+ *   shift       out[:, :, h, :] = in[:, :, h + shift, :], zero filled           (int(uniform(-r, r) * dim2), :34)
+ *   freq0/width in[:, :, :, freq0:freq0+width] = 0                              (:60-62)
+ *   time0/width in[:, :, time0:time0+width, :] = 0                              (:76-78)
+ *   noise       + noise_level * N(0,1), Philox4x32-10 keyed by (noise_seed, element) -- same distribution as
+ *               torch.randn_like (:46), not the same stream
+ * normalize != 0 applies db_normalize(ref_db) last: clamp((x - ref_db) / -ref_db, 0, 1).
+ * A non-zero shift cannot run in place (d_in == d_out).
+ * ------------------------------------------------------------------------------------------------------------ */
+#define GTC_AUG_TIME_SHIFT 1
+#define GTC_AUG_NOISE      2
+#define GTC_AUG_FREQ_MASK  3
+#define GTC_AUG_TIME_MASK  4
+int gtc_augment_batch(const float* d_in, float* d_out, int64_t batch, int channels, int dim2, int dim3,
+                      const int* h_ops, int n_ops, int shift, int freq0, int freq_width, int time0, int time_width,
+                      float noise_level, uint64_t noise_seed, int normalize, float ref_db, gtc_stream_t stream);
+/* ViT_engine.py:112-117 and "tablature-generator (1).py":334-335: d_out[i] = clamp((d_in[i] - ref_db) / -ref_db, 0, 1);
+ * in place allowed. */
+int gtc_db_normalize(const float* d_in, int64_t n, float ref_db, float* d_out, gtc_stream_t stream);
 
 #ifdef __cplusplus
 }

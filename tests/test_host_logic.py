@@ -129,3 +129,54 @@ def test_stats_gather_world_size_2_gloo():
     assert res[0][1] == res[1][1]                                  # every rank sees the same [2, 8] table
     tot = res[0][2]
     assert tot["n_clips"] == 7 and tot["total"] == 30 and tot["with_notes"] == 5 and tot["elapsed_ns"] == 2000
+
+
+# ---------------------------------------------------------------------------------------------------- packed files
+def test_packed_files_explode_to_the_reference_layout(tmp_path):
+    from gtc_b200 import audio_io
+    rng = np.random.default_rng(0)
+    feats = rng.uniform(-120, 0, (13, 96, 5)).astype(np.float32)
+    tabs = (rng.random((13, 6, 19)) < 0.05).astype(np.int8)
+    keep = np.array([0, 1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 12, 13])            # segment 4 had no picture (:307-309)
+    fp = tmp_path / ("clipA" + audio_io.FEATURE_PACK_SUFFIX)
+    lp = tmp_path / ("clipA" + audio_io.LABEL_PACK_SUFFIX)
+    audio_io.save_features_packed(fp, feats)
+    audio_io.save_labels_packed(lp, tabs, keep)
+    assert audio_io.explode_features(fp, tmp_path / "f") == 13
+    assert audio_io.explode_labels(lp, tmp_path / "l") == 13
+    for k in range(13):
+        a = np.load(tmp_path / "f" / f"clipA_segment_{k}.npy")
+        assert a.dtype == np.float32 and a.shape == (96, 5) and a.flags.f_contiguous and np.array_equal(a, feats[k])
+        b = np.load(tmp_path / "l" / "clipA" / f"clipA_{keep[k]:04d}.npy")
+        assert b.dtype == np.int8 and b.shape == (6, 19) and np.array_equal(b, tabs[k])
+    assert (tmp_path / "l" / "clipA" / "clipA_0000.npy").stat().st_size == 242          # the reference's 242-byte file
+
+
+def test_loader_reads_packed_and_exploded_dirs_identically(tmp_path):
+    """sorted(listdir) pairing order (un-padded counters sort _10 before _2) is kept for packed files."""
+    from gtc_b200 import audio_io, loaders
+    rng = np.random.default_rng(1)
+    packed, flat = tmp_path / "packed", tmp_path / "flat"
+    packed.mkdir(); flat.mkdir()
+    for base, n in (("b_clip", 12), ("a_clip", 3)):
+        feats = rng.uniform(-120, 0, (n, 96, 5)).astype(np.float32)
+        p = packed / (base + audio_io.FEATURE_PACK_SUFFIX)
+        audio_io.save_features_packed(p, feats)
+        audio_io.explode_features(p, flat)
+    n1, a1 = loaders.load_feature_dir(str(packed))
+    n2, a2 = loaders.load_feature_dir(str(flat))
+    assert n1 == n2 == sorted(n2) and np.array_equal(a1, a2)
+    assert n1.index("b_clip_segment_10.npy") < n1.index("b_clip_segment_2.npy")
+
+
+def test_inference_segment_tables():
+    """tablature_generator.py:655-664 and "tablature-generator (1).py":299-323 window arithmetic."""
+    from gtc_b200 import inference
+    starts, valid = inference.segment_table(100000, 66150, 33075)
+    assert starts.tolist() == [0, 33075, 66150, 99225] and valid.tolist() == [66150, 66150, 33850, 775]
+    s, v, L = inference.vit_window_table(44100, 44100)
+    assert L == 8820 and len(s) == 9 and s[-1] == 8 * 4410 and set(v.tolist()) == {8820}
+    s, v, L = inference.vit_window_table(5000, 44100)                  # shorter than a window but >= half: one padded window
+    assert s.tolist() == [0] and v.tolist() == [5000]
+    s, v, L = inference.vit_window_table(4000, 44100)                  # shorter than half a window: skipped (:317-318)
+    assert len(s) == 0
