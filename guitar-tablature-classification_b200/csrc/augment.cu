@@ -15,7 +15,7 @@ namespace gtc {
 
 struct AugParams {
   int n_ops;
-  int op[4];        // GTC_AUG_* in application order
+  unsigned ops;     // GTC_AUG_* codes in application order, 4 bits each (a packed word: no dynamic indexing of params)
   int shift;        // time_shift: out[h] = in[h + shift] (zero fill), along dim 2
   int f0, fw;       // frequency_mask: [:, :, :, f0:f0+fw] = 0   (dim 3)
   int t0, tw;       // time_mask:      [:, :, t0:t0+tw, :] = 0   (dim 2)
@@ -54,14 +54,22 @@ __device__ __forceinline__ void normal4(unsigned long long seed, unsigned long l
   }
 }
 
-// value of 4 consecutive columns w0..w0+3 of output row (bc, h)
-__device__ __forceinline__ float4 aug_quad(const float* __restrict__ in, const AugParams& a, int64_t bc, int h, int w0, int H, int W) {
-  float add[4] = {0.f, 0.f, 0.f, 0.f};
-  bool live[4] = {true, true, true, true};
+// Where the 4 consecutive columns w0..w0+3 of output row (bc, h) come from: walks the op list backwards.
+// Returns the source float4 index (or -1 when the whole quad is zero-filled), the per-column live mask and the noise sum.
+struct QuadPlan {
+  long long src;      // float4 index into the input, -1 = no load
+  unsigned live;      // bit j: column j still carries the input value
+  float add[4];
+};
+
+__device__ __forceinline__ QuadPlan aug_plan(const AugParams& a, long long bc, int h, int w0, int H, int W) {
+  QuadPlan q;
+  q.live = 0xfu;
+  q.add[0] = q.add[1] = q.add[2] = q.add[3] = 0.f;
   int hc = h;
   bool row_dead = false;
   for (int k = a.n_ops - 1; k >= 0 && !row_dead; --k) {
-    switch (a.op[k]) {
+    switch ((a.ops >> (4 * k)) & 15u) {
       case GTC_AUG_TIME_SHIFT:
         hc += a.shift;
         if (hc < 0 || hc >= H) row_dead = true;
@@ -71,42 +79,66 @@ __device__ __forceinline__ float4 aug_quad(const float* __restrict__ in, const A
         break;
       case GTC_AUG_FREQ_MASK:
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (w0 + j >= a.f0 && w0 + j < a.f0 + a.fw) live[j] = false;
+        for (int j = 0; j < 4; ++j) if (w0 + j >= a.f0 && w0 + j < a.f0 + a.fw) q.live &= ~(1u << j);
         break;
       case GTC_AUG_NOISE: {
         float z[4];
         normal4(a.seed, (unsigned long long)((bc * H + hc) * W + w0) >> 2, z);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (live[j]) add[j] += z[j] * a.noise_level;
+        for (int j = 0; j < 4; ++j) if (q.live & (1u << j)) q.add[j] += z[j] * a.noise_level;
         break;
       }
       default: break;
     }
   }
-  float v[4] = {0.f, 0.f, 0.f, 0.f};
-  if (!row_dead) {
-    const float4 x = __ldcs(reinterpret_cast<const float4*>(in + (bc * H + hc) * W + w0));
-    v[0] = live[0] ? x.x : 0.f; v[1] = live[1] ? x.y : 0.f; v[2] = live[2] ? x.z : 0.f; v[3] = live[3] ? x.w : 0.f;
-  }
-  float o[4];
+  q.src = (row_dead || q.live == 0u) ? -1 : ((bc * H + hc) * W + w0) >> 2;
+  if (row_dead) q.live = 0u;
+  return q;
+}
+
+__device__ __forceinline__ float4 aug_finish(const AugParams& a, const QuadPlan& q, float4 x) {
+  float o[4] = {(q.live & 1u) ? x.x : 0.f, (q.live & 2u) ? x.y : 0.f, (q.live & 4u) ? x.z : 0.f, (q.live & 8u) ? x.w : 0.f};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    o[j] = v[j] + add[j];
+    o[j] += q.add[j];
     if (a.normalize) o[j] = fminf(fmaxf((o[j] - a.ref_db) / (0.f - a.ref_db), 0.f), 1.f);
   }
   return make_float4(o[0], o[1], o[2], o[3]);
 }
 
+// Idx = unsigned (fast 32-bit div/mod) whenever the batch has < 2^31 quads.  Each thread owns kAugUnroll quads per
+// step, all loads issued before the first store (enough bytes in flight per SM to cover HBM latency).
+constexpr int kAugUnroll = 4;
+template <typename Idx>
 __global__ void __launch_bounds__(256)
-augment_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t BC, int H, int W, const AugParams a) {
-  const int wq = W >> 2;
-  const int64_t total = BC * H * wq;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i % wq);
-    const int64_t row = i / wq;
-    const int h = (int)(row % H);
-    const int64_t bc = row / H;
-    __stcs(reinterpret_cast<float4*>(out + row * W) + q, aug_quad(in, a, bc, h, q * 4, H, W));
+augment_kernel(const float* __restrict__ in, float* __restrict__ out, long long BC, int H, int W, const AugParams a) {
+  const Idx wq = (Idx)(W >> 2);
+  const Idx total = (Idx)(BC * H) * wq;
+  const Idx stride = (Idx)gridDim.x * blockDim.x;
+  const float4* in4 = reinterpret_cast<const float4*>(in);
+  float4* out4 = reinterpret_cast<float4*>(out);
+  for (Idx i0 = (Idx)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * kAugUnroll) {
+    QuadPlan q[kAugUnroll];
+    float4 x[kAugUnroll];
+#pragma unroll
+    for (int u = 0; u < kAugUnroll; ++u) {
+      const Idx i = i0 + (Idx)u * stride;
+      x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      q[u].src = -1;
+      if (i < total && i >= i0) {                       // i >= i0: no wrap-around of the 32-bit index
+        const Idx row = i / wq;
+        const int w0 = (int)(i - row * wq) << 2;
+        const Idx bc = row / (Idx)H;
+        const int h = (int)(row - bc * (Idx)H);
+        q[u] = aug_plan(a, (long long)bc, h, w0, H, W);
+        if (q[u].src >= 0) x[u] = __ldcs(in4 + q[u].src);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kAugUnroll; ++u) {
+      const Idx i = i0 + (Idx)u * stride;
+      if (i < total && i >= i0) __stcs(out4 + i, aug_finish(a, q[u], x[u]));
+    }
   }
 }
 
@@ -167,7 +199,7 @@ extern "C" int gtc_augment_batch(const float* d_in, float* d_out, int64_t batch,
   for (int k = 0; k < n_ops; ++k) {
     GTC_REQUIRE(h_ops[k] >= GTC_AUG_TIME_SHIFT && h_ops[k] <= GTC_AUG_TIME_MASK, GTC_E_ARG, "gtc_augment_batch: unknown op %d", h_ops[k]);
     for (int j = 0; j < k; ++j) GTC_REQUIRE(h_ops[j] != h_ops[k], GTC_E_ARG, "gtc_augment_batch: op %d listed twice", h_ops[k]);
-    a.op[k] = h_ops[k];
+    a.ops |= (unsigned)h_ops[k] << (4 * k);
     if (h_ops[k] == GTC_AUG_TIME_SHIFT && shift != 0) moves = true;
   }
   GTC_REQUIRE(!(moves && d_in == d_out), GTC_E_ARG, "gtc_augment_batch: a time shift cannot run in place");
@@ -179,7 +211,11 @@ extern "C" int gtc_augment_batch(const float* d_in, float* d_out, int64_t batch,
   const int64_t total = batch * channels * dim2 * (dim3 / 4);
   int64_t blocks = ceil_div(total, 256);
   if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
-  augment_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, batch * channels, dim2, dim3, a);
+  if (blocks > 1) blocks = ceil_div(ceil_div(total, kAugUnroll), 256) < blocks ? ceil_div(ceil_div(total, kAugUnroll), 256) : blocks;
+  if (total < 0x7fffffffLL - (int64_t)kAugUnroll * blocks * 256)
+    augment_kernel<unsigned><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, batch * channels, dim2, dim3, a);
+  else
+    augment_kernel<unsigned long long><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, batch * channels, dim2, dim3, a);
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;
 }

@@ -60,6 +60,34 @@ __device__ __host__ __forceinline__ int frames_of(int len, int hop, int n_oct) {
   return t;
 }
 
+// out[u + 256 r] = sum_a h[2a] * xe[u + 256 r + c - a] + h[2a+1] * xo[u + 256 r + c - a - 1],  r < NR: every tap pair is
+// fetched once (one broadcast LDS.64) and used for NR outputs; lanes read unit-stride from the de-interleaved phases.
+template <int NR>
+__device__ __forceinline__ void fir_rows(const float* __restrict__ sh, const float* __restrict__ xe, const float* __restrict__ xo,
+                                         int c, int u0, int n_here, float gain, float* __restrict__ y) {
+  float acc[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) acc[r] = 0.f;
+  const float* pe = xe + u0 + c;
+  const float* po = xo + u0 + c - 1;
+  const float2* h2 = reinterpret_cast<const float2*>(sh);
+#pragma unroll 4
+  for (int a = 0; a < c; ++a) {
+    const float2 h = h2[a];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      acc[r] = fmaf(h.x, pe[r * 256 - a], acc[r]);
+      acc[r] = fmaf(h.y, po[r * 256 - a], acc[r]);
+    }
+  }
+  const float hl = sh[2 * c];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    acc[r] = fmaf(hl, pe[r * 256 - c], acc[r]);
+    if (u0 + r * 256 < n_here) y[u0 + r * 256] = acc[r] * gain;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // 2:1 decimator.  blockIdx.x = segment * tiles + tile.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -86,37 +114,22 @@ decimate2_kernel(const In* __restrict__ src, const int64_t* __restrict__ seg_sta
   for (int j = threadIdx.x; j < n_taps; j += blockDim.x) sh[j] = __ldg(taps + j);
   if (threadIdx.x == 0) sh[n_taps] = 0.f;
   const int base = 2 * k0 - c;                     // input index of xe[0]
-  for (int m = threadIdx.x; m < 2 * span; m += blockDim.x) {
+  const int n_here = min(kDecTile, len_out - k0);  // outputs this CTA really owes (short octaves fill a fraction of a tile)
+  for (int m = threadIdx.x; m < 2 * (n_here + c + 1); m += blockDim.x) {
     const int i = base + m;
     const float v = (i >= 0 && i < readable) ? s_load(x + i) : 0.f;
     if (m & 1) xo[m >> 1] = v; else xe[m >> 1] = v;
   }
   __syncthreads();
-
-  // out[k0+u] = sum_a h[2a] * xe[u + c - a] + h[2a+1] * xo[u + c - a - 1]
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   const int u0 = threadIdx.x;
-  const float* pe = xe + u0 + c;
-  const float* po = xo + u0 + c - 1;
-#pragma unroll 4
-  for (int a = 0; a < c; ++a) {
-    const float he = sh[2 * a], ho = sh[2 * a + 1];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      acc[r] = fmaf(he, pe[r * 256 - a], acc[r]);
-      acc[r] = fmaf(ho, po[r * 256 - a], acc[r]);
-    }
-  }
-  {
-    const float he = sh[2 * c];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) acc[r] = fmaf(he, pe[r * 256 - c], acc[r]);
-  }
-  float* y = dst + s * dst_stride;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int k = k0 + u0 + r * 256;
-    if (k < len_out) y[k] = acc[r] * gain;
+  if ((u0 & ~31) >= n_here) return;                // whole warp past the end of the signal
+  float* y = dst + s * dst_stride + k0;
+  const int nr = (n_here + 255) >> 8;              // 256-output groups in use: 1..4
+  switch (nr) {
+    case 1: fir_rows<1>(sh, xe, xo, c, u0, n_here, gain, y); break;
+    case 2: fir_rows<2>(sh, xe, xo, c, u0, n_here, gain, y); break;
+    case 3: fir_rows<3>(sh, xe, xo, c, u0, n_here, gain, y); break;
+    default: fir_rows<4>(sh, xe, xo, c, u0, n_here, gain, y); break;
   }
 }
 
