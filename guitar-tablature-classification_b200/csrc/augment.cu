@@ -13,15 +13,22 @@
 
 namespace gtc {
 
+// The reference applies its ops in a drawn order; the host resolves that order ONCE into output-space facts, so the
+// kernel is straight-line code per element:
+//   value  = in[h + shift][w]        unless the shifted row leaves [0, H), or h is in the (output-space) time-mask rows
+//                                    [t0, t1), or w is in the frequency-mask columns [f0, f1)
+//   noise  = level * N(0,1) keyed by the coordinate the element had when add_noise ran (row h + noise_row_off); it
+//            survives a mask / an out-of-range shift only if that op ran BEFORE add_noise
 struct AugParams {
-  int n_ops;
-  unsigned ops;     // GTC_AUG_* codes in application order, 4 bits each (a packed word: no dynamic indexing of params)
-  int shift;        // time_shift: out[h] = in[h + shift] (zero fill), along dim 2
-  int f0, fw;       // frequency_mask: [:, :, :, f0:f0+fw] = 0   (dim 3)
-  int t0, tw;       // time_mask:      [:, :, t0:t0+tw, :] = 0   (dim 2)
+  int shift;            // 0 when no time_shift
+  int t0, t1;           // output rows zeroed by time_mask (already moved by a later shift), empty when t1 <= t0
+  int f0, f1;           // columns zeroed by frequency_mask
+  int has_noise;
+  int noise_row_off;    // shift if the shift runs after add_noise (noise travels with the rows), else 0
+  int noise_dies_tmask, noise_dies_fmask, noise_dies_shift;   // the op runs after add_noise
   float noise_level;
   unsigned long long seed;
-  int normalize;    // db_normalize after the ops
+  int normalize;        // db_normalize after the ops
   float ref_db;
 };
 
@@ -54,90 +61,60 @@ __device__ __forceinline__ void normal4(unsigned long long seed, unsigned long l
   }
 }
 
-// Where the 4 consecutive columns w0..w0+3 of output row (bc, h) come from: walks the op list backwards.
-// Returns the source float4 index (or -1 when the whole quad is zero-filled), the per-column live mask and the noise sum.
-struct QuadPlan {
-  long long src;      // float4 index into the input, -1 = no load
-  unsigned live;      // bit j: column j still carries the input value
-  float add[4];
-};
-
-__device__ __forceinline__ QuadPlan aug_plan(const AugParams& a, long long bc, int h, int w0, int H, int W) {
-  QuadPlan q;
-  q.live = 0xfu;
-  q.add[0] = q.add[1] = q.add[2] = q.add[3] = 0.f;
-  int hc = h;
-  bool row_dead = false;
-  for (int k = a.n_ops - 1; k >= 0 && !row_dead; --k) {
-    switch ((a.ops >> (4 * k)) & 15u) {
-      case GTC_AUG_TIME_SHIFT:
-        hc += a.shift;
-        if (hc < 0 || hc >= H) row_dead = true;
-        break;
-      case GTC_AUG_TIME_MASK:
-        if (hc >= a.t0 && hc < a.t0 + a.tw) row_dead = true;
-        break;
-      case GTC_AUG_FREQ_MASK:
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (w0 + j >= a.f0 && w0 + j < a.f0 + a.fw) q.live &= ~(1u << j);
-        break;
-      case GTC_AUG_NOISE: {
-        float z[4];
-        normal4(a.seed, (unsigned long long)((bc * H + hc) * W + w0) >> 2, z);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (q.live & (1u << j)) q.add[j] += z[j] * a.noise_level;
-        break;
-      }
-      default: break;
-    }
-  }
-  q.src = (row_dead || q.live == 0u) ? -1 : ((bc * H + hc) * W + w0) >> 2;
-  if (row_dead) q.live = 0u;
-  return q;
-}
-
-__device__ __forceinline__ float4 aug_finish(const AugParams& a, const QuadPlan& q, float4 x) {
-  float o[4] = {(q.live & 1u) ? x.x : 0.f, (q.live & 2u) ? x.y : 0.f, (q.live & 4u) ? x.z : 0.f, (q.live & 8u) ? x.w : 0.f};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    o[j] += q.add[j];
-    if (a.normalize) o[j] = fminf(fmaxf((o[j] - a.ref_db) / (0.f - a.ref_db), 0.f), 1.f);
-  }
-  return make_float4(o[0], o[1], o[2], o[3]);
-}
-
-// Idx = unsigned (fast 32-bit div/mod) whenever the batch has < 2^31 quads.  Each thread owns kAugUnroll quads per
-// step, all loads issued before the first store (enough bytes in flight per SM to cover HBM latency).
-constexpr int kAugUnroll = 4;
-template <typename Idx>
+// One thread = one float4 (4 columns) of kAugRows rows spaced `row_step` apart; all loads are issued before the first
+// store so every SM keeps enough bytes in flight to cover HBM latency.  blockDim = (quads per row | 256-cap, rows).
+constexpr int kAugRows = 4;
 __global__ void __launch_bounds__(256)
-augment_kernel(const float* __restrict__ in, float* __restrict__ out, long long BC, int H, int W, const AugParams a) {
-  const Idx wq = (Idx)(W >> 2);
-  const Idx total = (Idx)(BC * H) * wq;
-  const Idx stride = (Idx)gridDim.x * blockDim.x;
+augment_kernel(const float* __restrict__ in, float* __restrict__ out, unsigned n_rows, int H, int W, const AugParams a) {
+  const int wq = W >> 2;
+  const unsigned row_step = gridDim.x * blockDim.y;
   const float4* in4 = reinterpret_cast<const float4*>(in);
   float4* out4 = reinterpret_cast<float4*>(out);
-  for (Idx i0 = (Idx)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * kAugUnroll) {
-    QuadPlan q[kAugUnroll];
-    float4 x[kAugUnroll];
+  for (unsigned row0 = blockIdx.x * blockDim.y + threadIdx.y; row0 < n_rows; row0 += row_step * kAugRows) {
+    for (int q = threadIdx.x; q < wq; q += blockDim.x) {
+      const int w0 = q << 2;
+      unsigned colmask = 0xfu;                                   // bit j: column w0+j keeps its value
 #pragma unroll
-    for (int u = 0; u < kAugUnroll; ++u) {
-      const Idx i = i0 + (Idx)u * stride;
-      x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      q[u].src = -1;
-      if (i < total && i >= i0) {                       // i >= i0: no wrap-around of the 32-bit index
-        const Idx row = i / wq;
-        const int w0 = (int)(i - row * wq) << 2;
-        const Idx bc = row / (Idx)H;
-        const int h = (int)(row - bc * (Idx)H);
-        q[u] = aug_plan(a, (long long)bc, h, w0, H, W);
-        if (q[u].src >= 0) x[u] = __ldcs(in4 + q[u].src);
+      for (int j = 0; j < 4; ++j) if (w0 + j >= a.f0 && w0 + j < a.f1) colmask &= ~(1u << j);
+      float4 x[kAugRows];
+      bool keep[kAugRows], nz[kAugRows];
+      unsigned bc[kAugRows];
+      int h[kAugRows];
+#pragma unroll
+      for (int r = 0; r < kAugRows; ++r) {
+        const unsigned row = row0 + r * row_step;
+        x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        keep[r] = nz[r] = false;
+        bc[r] = 0; h[r] = 0;
+        if (row < n_rows) {
+          bc[r] = row / (unsigned)H;
+          h[r] = (int)(row - bc[r] * (unsigned)H);
+          const int hs = h[r] + a.shift;
+          const bool in_range = hs >= 0 && hs < H;
+          const bool masked = h[r] >= a.t0 && h[r] < a.t1;
+          keep[r] = in_range && !masked;
+          nz[r] = a.has_noise && !(masked && a.noise_dies_tmask) && !(!in_range && a.noise_dies_shift);
+          if (keep[r] && colmask) x[r] = __ldcs(in4 + ((size_t)bc[r] * H + hs) * wq + q);
+        }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < kAugUnroll; ++u) {
-      const Idx i = i0 + (Idx)u * stride;
-      if (i < total && i >= i0) __stcs(out4 + i, aug_finish(a, q[u], x[u]));
+      for (int r = 0; r < kAugRows; ++r) {
+        const unsigned row = row0 + r * row_step;
+        if (row >= n_rows) continue;
+        float o[4] = {(colmask & 1u) ? x[r].x : 0.f, (colmask & 2u) ? x[r].y : 0.f, (colmask & 4u) ? x[r].z : 0.f, (colmask & 8u) ? x[r].w : 0.f};
+        if (nz[r]) {
+          float z[4];
+          normal4(a.seed, ((unsigned long long)bc[r] * H + (h[r] + a.noise_row_off)) * wq + q, z);
+          const unsigned nm = a.noise_dies_fmask ? colmask : 0xfu;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (nm & (1u << j)) o[j] += z[j] * a.noise_level;
+        }
+        if (a.normalize) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = fminf(fmaxf((o[j] - a.ref_db) / (0.f - a.ref_db), 0.f), 1.f);
+        }
+        __stcs(out4 + (size_t)row * wq + q, make_float4(o[0], o[1], o[2], o[3]));
+      }
     }
   }
 }
@@ -192,30 +169,44 @@ extern "C" int gtc_augment_batch(const float* d_in, float* d_out, int64_t batch,
   GTC_REQUIRE(((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0, GTC_E_ARG,
               "gtc_augment_batch: buffers must be 16-byte aligned");
   GTC_REQUIRE(!normalize || ref_db < 0.f, GTC_E_ARG, "gtc_augment_batch: ref_db must be negative");
-  AugParams a;
-  memset(&a, 0, sizeof(a));
-  a.n_ops = n_ops;
-  bool moves = false;
+  GTC_REQUIRE(freq_width >= 0 && time_width >= 0, GTC_E_ARG, "gtc_augment_batch: negative mask width");
+  GTC_REQUIRE(batch * channels * dim2 < 0xffffffffLL, GTC_E_UNSUP, "gtc_augment_batch: more than 2^32 rows; split the batch");
+  // resolve the drawn order into output-space facts (see AugParams)
+  int pos[5] = {-1, -1, -1, -1, -1};
   for (int k = 0; k < n_ops; ++k) {
     GTC_REQUIRE(h_ops[k] >= GTC_AUG_TIME_SHIFT && h_ops[k] <= GTC_AUG_TIME_MASK, GTC_E_ARG, "gtc_augment_batch: unknown op %d", h_ops[k]);
-    for (int j = 0; j < k; ++j) GTC_REQUIRE(h_ops[j] != h_ops[k], GTC_E_ARG, "gtc_augment_batch: op %d listed twice", h_ops[k]);
-    a.ops |= (unsigned)h_ops[k] << (4 * k);
-    if (h_ops[k] == GTC_AUG_TIME_SHIFT && shift != 0) moves = true;
+    GTC_REQUIRE(pos[h_ops[k]] < 0, GTC_E_ARG, "gtc_augment_batch: op %d listed twice", h_ops[k]);
+    pos[h_ops[k]] = k;
   }
-  GTC_REQUIRE(!(moves && d_in == d_out), GTC_E_ARG, "gtc_augment_batch: a time shift cannot run in place");
-  GTC_REQUIRE(freq_width >= 0 && time_width >= 0, GTC_E_ARG, "gtc_augment_batch: negative mask width");
-  a.shift = shift; a.f0 = freq0; a.fw = freq_width; a.t0 = time0; a.tw = time_width;
+  AugParams a;
+  memset(&a, 0, sizeof(a));
+  const int p_shift = pos[GTC_AUG_TIME_SHIFT], p_noise = pos[GTC_AUG_NOISE], p_f = pos[GTC_AUG_FREQ_MASK], p_t = pos[GTC_AUG_TIME_MASK];
+  a.shift = p_shift >= 0 ? shift : 0;
+  GTC_REQUIRE(!(a.shift != 0 && d_in == d_out), GTC_E_ARG, "gtc_augment_batch: a time shift cannot run in place");
+  if (p_t >= 0 && time_width > 0) {
+    // a mask applied before the shift travels with the rows: source rows [t0, t0+tw) land on output rows [t0 - shift, ...)
+    const int move = (p_shift > p_t) ? a.shift : 0;
+    a.t0 = time0 - move;
+    a.t1 = time0 + time_width - move;
+  }
+  if (p_f >= 0 && freq_width > 0) { a.f0 = freq0; a.f1 = freq0 + freq_width; }
+  if (p_noise >= 0) {
+    a.has_noise = 1;
+    a.noise_row_off = (p_shift > p_noise) ? a.shift : 0;
+    a.noise_dies_tmask = p_t > p_noise;
+    a.noise_dies_fmask = p_f > p_noise;
+    a.noise_dies_shift = p_shift > p_noise;
+  }
   a.noise_level = noise_level; a.seed = noise_seed; a.normalize = normalize ? 1 : 0; a.ref_db = ref_db;
   const int sms = sm_count_of_current_device();
   if (sms <= 0) return GTC_E_CUDA;
-  const int64_t total = batch * channels * dim2 * (dim3 / 4);
-  int64_t blocks = ceil_div(total, 256);
+  const int wq = dim3 / 4;
+  const unsigned n_rows = (unsigned)(batch * channels * dim2);
+  ::dim3 block((unsigned)(wq < 256 ? wq : 256), 1, 1);
+  block.y = 256 / block.x > 0 ? 256 / block.x : 1;
+  int64_t blocks = ceil_div(ceil_div((int64_t)n_rows, kAugRows), block.y);
   if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
-  if (blocks > 1) blocks = ceil_div(ceil_div(total, kAugUnroll), 256) < blocks ? ceil_div(ceil_div(total, kAugUnroll), 256) : blocks;
-  if (total < 0x7fffffffLL - (int64_t)kAugUnroll * blocks * 256)
-    augment_kernel<unsigned><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, batch * channels, dim2, dim3, a);
-  else
-    augment_kernel<unsigned long long><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, batch * channels, dim2, dim3, a);
+  augment_kernel<<<(unsigned)blocks, block, 0, (cudaStream_t)stream>>>(d_in, d_out, n_rows, dim2, dim3, a);
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;
 }

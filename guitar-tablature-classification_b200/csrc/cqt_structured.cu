@@ -60,48 +60,44 @@ __device__ __host__ __forceinline__ int frames_of(int len, int hop, int n_oct) {
   return t;
 }
 
-// out[u + 256 r] = sum_a h[2a] * xe[u + 256 r + c - a] + h[2a+1] * xo[u + 256 r + c - a - 1],  r < NR: every tap pair is
-// fetched once (one broadcast LDS.64) and used for NR outputs; lanes read unit-stride from the de-interleaved phases.
-template <int NR>
-__device__ __forceinline__ void fir_rows(const float* __restrict__ sh, const float* __restrict__ xe, const float* __restrict__ xo,
-                                         int c, int u0, int n_here, float gain, float* __restrict__ y) {
-  float acc[NR];
-#pragma unroll
-  for (int r = 0; r < NR; ++r) acc[r] = 0.f;
-  const float* pe = xe + u0 + c;
-  const float* po = xo + u0 + c - 1;
-  const float2* h2 = reinterpret_cast<const float2*>(sh);
-#pragma unroll 4
-  for (int a = 0; a < c; ++a) {
-    const float2 h = h2[a];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      acc[r] = fmaf(h.x, pe[r * 256 - a], acc[r]);
-      acc[r] = fmaf(h.y, po[r * 256 - a], acc[r]);
-    }
-  }
-  const float hl = sh[2 * c];
-#pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    acc[r] = fmaf(hl, pe[r * 256 - c], acc[r]);
-    if (u0 + r * 256 < n_here) y[u0 + r * 256] = acc[r] * gain;
+// ---------------------------------------------------------------------------------------------------------------------
+// 2:1 decimator.  blockIdx.x = segment * tiles + tile.
+//
+// With xe[m] = x[2 k0 - c + 2m], xo[m] = x[2 k0 - c + 2m + 1] (the two input phases, de-interleaved while staging) and
+// the taps re-indexed he[j] = h[2(c-j)], ho[j] = h[2(c-1-j)+1], both phases are plain correlations
+//     out[k0+u] = sum_j he[j] xe[u+j] + sum_j ho[j] xo[u+j].
+// A thread owns 4 consecutive outputs and walks the taps 4 at a time with an 8-sample register window: per block ONE
+// LDS.128 of samples (lanes 16 B apart: conflict-free) and ONE broadcast LDS.128 of taps feed 16 FFMA, so the loop is
+// bound by FFMA issue, not by shared-memory bandwidth (the first version spent 9 shared wavefronts per 8 FFMA and sat
+// at 99 % l1tex throughput, profiles/r01e).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void corr4(const float4* __restrict__ x4, const float4* __restrict__ t4, int n_blocks, float (&acc)[4]) {
+  float4 w0 = x4[0];
+#pragma unroll 2
+  for (int jb = 0; jb < n_blocks; ++jb) {
+    const float4 w1 = x4[jb + 1];
+    const float4 t = t4[jb];
+    acc[0] = fmaf(t.x, w0.x, acc[0]); acc[0] = fmaf(t.y, w0.y, acc[0]); acc[0] = fmaf(t.z, w0.z, acc[0]); acc[0] = fmaf(t.w, w0.w, acc[0]);
+    acc[1] = fmaf(t.x, w0.y, acc[1]); acc[1] = fmaf(t.y, w0.z, acc[1]); acc[1] = fmaf(t.z, w0.w, acc[1]); acc[1] = fmaf(t.w, w1.x, acc[1]);
+    acc[2] = fmaf(t.x, w0.z, acc[2]); acc[2] = fmaf(t.y, w0.w, acc[2]); acc[2] = fmaf(t.z, w1.x, acc[2]); acc[2] = fmaf(t.w, w1.y, acc[2]);
+    acc[3] = fmaf(t.x, w0.w, acc[3]); acc[3] = fmaf(t.y, w1.x, acc[3]); acc[3] = fmaf(t.z, w1.y, acc[3]); acc[3] = fmaf(t.w, w1.z, acc[3]);
+    w0 = w1;
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// 2:1 decimator.  blockIdx.x = segment * tiles + tile.
-// ---------------------------------------------------------------------------------------------------------------------
 template <typename In>
 __global__ void __launch_bounds__(256)
 decimate2_kernel(const In* __restrict__ src, const int64_t* __restrict__ seg_start, const int32_t* __restrict__ seg_valid,
                  const int32_t* __restrict__ seg_len, int stage, int64_t src_stride, float* __restrict__ dst,
                  int64_t dst_stride, const float* __restrict__ taps, int n_taps, int tiles, float gain) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int c = (n_taps - 1) >> 1;                 // even: n_taps == 1 (mod 4)
-  const int span = kDecTile + c + 1;
-  float* sh = sm;                                  // [n_taps + 1]
-  float* xe = sh + ((n_taps + 4) & ~3);            // even-phase inputs
-  float* xo = xe + ((span + 3) & ~3);              // odd-phase inputs
+  const int nt = (c + 4) & ~3;                     // taps per phase, padded to a multiple of 4 (c+1 even-phase taps)
+  const int span = kDecTile + nt + 4;              // staged samples per phase
+  float* he = sm;                                  // [nt]
+  float* ho = he + nt;                             // [nt]
+  float* xe = ho + nt;                             // [span]
+  float* xo = xe + span;                           // [span]
   const int64_t s = blockIdx.x / tiles;
   const int tile = blockIdx.x - (int)(s * tiles);
   const int len_in = halved(__ldg(seg_len + s), stage);
@@ -111,26 +107,28 @@ decimate2_kernel(const In* __restrict__ src, const int64_t* __restrict__ seg_sta
   const int readable = stage == 0 ? min(len_in, __ldg(seg_valid + s)) : len_in;
   const In* x = src + (seg_start ? __ldg(seg_start + s) : s * src_stride);
 
-  for (int j = threadIdx.x; j < n_taps; j += blockDim.x) sh[j] = __ldg(taps + j);
-  if (threadIdx.x == 0) sh[n_taps] = 0.f;
+  for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+    he[j] = j <= c ? __ldg(taps + 2 * (c - j)) : 0.f;
+    ho[j] = j < c ? __ldg(taps + 2 * (c - 1 - j) + 1) : 0.f;
+  }
   const int base = 2 * k0 - c;                     // input index of xe[0]
   const int n_here = min(kDecTile, len_out - k0);  // outputs this CTA really owes (short octaves fill a fraction of a tile)
-  for (int m = threadIdx.x; m < 2 * (n_here + c + 1); m += blockDim.x) {
+  const int n_stage = ((n_here + 3) & ~3) + nt + 4;
+  for (int m = threadIdx.x; m < 2 * n_stage; m += blockDim.x) {
     const int i = base + m;
     const float v = (i >= 0 && i < readable) ? s_load(x + i) : 0.f;
     if (m & 1) xo[m >> 1] = v; else xe[m >> 1] = v;
   }
   __syncthreads();
-  const int u0 = threadIdx.x;
-  if ((u0 & ~31) >= n_here) return;                // whole warp past the end of the signal
-  float* y = dst + s * dst_stride + k0;
-  const int nr = (n_here + 255) >> 8;              // 256-output groups in use: 1..4
-  switch (nr) {
-    case 1: fir_rows<1>(sh, xe, xo, c, u0, n_here, gain, y); break;
-    case 2: fir_rows<2>(sh, xe, xo, c, u0, n_here, gain, y); break;
-    case 3: fir_rows<3>(sh, xe, xo, c, u0, n_here, gain, y); break;
-    default: fir_rows<4>(sh, xe, xo, c, u0, n_here, gain, y); break;
-  }
+  const int u = threadIdx.x << 2;
+  if (u >= n_here) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  corr4(reinterpret_cast<const float4*>(xe) + threadIdx.x, reinterpret_cast<const float4*>(he), nt >> 2, acc);
+  corr4(reinterpret_cast<const float4*>(xo) + threadIdx.x, reinterpret_cast<const float4*>(ho), nt >> 2, acc);
+  float* y = dst + s * dst_stride + k0 + u;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    if (u + r < n_here) y[r] = acc[r] * gain;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -265,6 +263,11 @@ sfinish_kernel(float* __restrict__ io, const float* __restrict__ segmax, int64_t
   }
 }
 
+static inline size_t dec_smem_bytes(int n_taps) {
+  const int c = (n_taps - 1) / 2, nt = (c + 4) & ~3;
+  return (size_t)(2 * nt + 2 * (kDecTile + nt + 4)) * sizeof(float);
+}
+
 struct SWorkspace {
   OctaveBufs bufs;
   size_t off_segmax, total;
@@ -297,8 +300,7 @@ static int run_structured(const SPlanImpl& p, const In* d_audio, const int64_t* 
   if (!complex_out) GTC_CUDA_CHECK(cudaMemsetAsync(segmax, 0, (size_t)n_seg * sizeof(float), st));
 
   // decimation chain: octave i+1 from octave i
-  const int c = (p.n_taps - 1) / 2;
-  const size_t dec_smem = (size_t)(((p.n_taps + 4) & ~3) + 2 * ((kDecTile + c + 1 + 3) & ~3)) * sizeof(float);
+  const size_t dec_smem = dec_smem_bytes(p.n_taps);
   int64_t len = max_len;
   for (int i = 0; i + 1 < p.n_oct; ++i) {
     const int64_t out_len = (len + 1) / 2;
@@ -386,7 +388,7 @@ extern "C" int gtc_scqt_plan_create(gtc_splan** out, int device, int n_octaves, 
     p.bin_lo[i] = lo; p.bin_cnt[i] = hi - lo;
   }
   const size_t resp_smem = ((size_t)p.n_fft * p.groups * 4 + (size_t)kFramesPerCta * (p.n_fft + 1) + 192) * sizeof(float);
-  const size_t dec_smem = (size_t)(((n_taps + 4) & ~3) + 2 * ((kDecTile + (n_taps - 1) / 2 + 1 + 3) & ~3)) * sizeof(float);
+  const size_t dec_smem = dec_smem_bytes(n_taps);
   if (resp_smem > 227 * 1024 || dec_smem > 227 * 1024) {
     delete plan;
     set_error("gtc_scqt_plan_create: n_fft %d x %d filters needs %zu B of shared memory (> 227 KB)", n_fft, filters_per_octave, resp_smem);
@@ -485,8 +487,7 @@ extern "C" int gtc_scqt_decimate(const gtc_splan* plan, const void* d_audio, int
   GTC_REQUIRE(d_audio && d_seg_start && d_seg_valid && d_seg_len && d_out, GTC_E_ARG, "gtc_scqt_decimate: null pointer");
   GTC_REQUIRE(out_stride >= (max_len + 1) / 2, GTC_E_ARG, "gtc_scqt_decimate: out_stride smaller than ceil(max_len/2)");
   const SPlanImpl& p = plan->impl;
-  const int c = (p.n_taps - 1) / 2;
-  const size_t dec_smem = (size_t)(((p.n_taps + 4) & ~3) + 2 * ((kDecTile + c + 1 + 3) & ~3)) * sizeof(float);
+  const size_t dec_smem = dec_smem_bytes(p.n_taps);
   const int tiles = (int)ceil_div((max_len + 1) / 2, kDecTile);
   const int64_t blocks = n_seg * tiles;
   GTC_REQUIRE(blocks < 0x7fffffffLL, GTC_E_ARG, "gtc_scqt_decimate: too many tiles; split the batch");
