@@ -271,12 +271,14 @@ extern "C" int gtc_cqt_contract_db(const gtc_plan* plan, const int64_t* d_clip_o
 }
 
 static int g_patch_max_ctas = 0;
-namespace gtc { int patch_max_ctas() { return g_patch_max_ctas; } }
+static int g_patch_ctas_per_sm = 2;
+namespace gtc { int patch_max_ctas() { return g_patch_max_ctas; } int patch_ctas_per_sm() { return g_patch_ctas_per_sm; } }
 
 extern "C" int gtc_set_option(int option, int value) {
   GTC_REQUIRE(value >= 0, GTC_E_ARG, "gtc_set_option: negative value");
   switch (option) {
     case GTC_OPT_PATCH_MAX_CTAS: g_patch_max_ctas = value; return GTC_OK;
+    case GTC_OPT_PATCH_CTAS_PER_SM: g_patch_ctas_per_sm = value > 0 ? value : 2; return GTC_OK;
     default: set_error("gtc_set_option: unknown option %d", option); return GTC_E_ARG;
   }
 }

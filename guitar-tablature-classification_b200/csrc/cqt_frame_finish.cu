@@ -45,33 +45,43 @@ __device__ __forceinline__ void split_store(float* hi, float* lo, int64_t i, con
 __device__ __forceinline__ float load_sample(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float load_sample(const int16_t* p) { return (float)__ldg(p) * (1.f / 32768.f); }
 
+// one warp per audio row: lane 0 finds the owning clip once (the first version searched per float4: 552 binary searches
+// per row), then the warp streams the row's kp/4 vectors
 template <typename T, typename In>
 __global__ void __launch_bounds__(256)
 frame_kernel(const In* __restrict__ audio, const int64_t* __restrict__ clip_off, const int64_t* __restrict__ seg_off,
              int n_clips, int parts, int row_len, int seg_hop, int kp, int64_t n_rows, int64_t n_rows_alloc,
              T* __restrict__ xhi, T* __restrict__ xlo, float scale, float* __restrict__ rowmax, int64_t n_rowmax) {
   const int vec_per_row = kp >> 2;
-  const int64_t total = n_rows_alloc * vec_per_row;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / vec_per_row;
-    const int k0 = (int)(i - row * vec_per_row) << 2;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows_alloc; row += warps_total) {
+    int64_t base = 0, clip_end = 0;                 // clip_end == 0: a padding row, all zeros
     if (row < n_rows) {
-      // clip of this row: rows of clip c start at seg_off[c] + c*(P-1)
-      int lo = 0, hi = n_clips;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(seg_off + mid) + (int64_t)mid * (parts - 1) <= row) lo = mid; else hi = mid;
+      if (lane == 0) {
+        // clip of this row: rows of clip c start at seg_off[c] + c*(P-1)
+        int lo = 0, hi = n_clips;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(seg_off + mid) + (int64_t)mid * (parts - 1) <= row) lo = mid; else hi = mid;
+        }
+        const int64_t r = row - (__ldg(seg_off + lo) + (int64_t)lo * (parts - 1));
+        clip_end = __ldg(clip_off + lo + 1);
+        base = __ldg(clip_off + lo) + r * seg_hop;
       }
-      const int64_t r = row - (__ldg(seg_off + lo) + (int64_t)lo * (parts - 1));
-      const int64_t clip_end = __ldg(clip_off + lo + 1);
-      const int64_t base = __ldg(clip_off + lo) + r * seg_hop + k0;
+      base = __shfl_sync(0xffffffffu, base, 0);
+      clip_end = __shfl_sync(0xffffffffu, clip_end, 0);
+    }
+    const int64_t out0 = row * vec_per_row;
+    for (int q = lane; q < vec_per_row; q += 32) {
+      const int k0 = q << 2;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (k0 + j < row_len && base + j < clip_end) v[j] = load_sample(audio + base + j);
+        if (k0 + j < row_len && base + k0 + j < clip_end) v[j] = load_sample(audio + base + k0 + j);
+      split_store(xhi, xlo, out0 + q, v, scale);
     }
-    split_store(xhi, xlo, i, v, scale);
-    if (k0 == 0 && row < n_rowmax) rowmax[row] = 0.f;
+    if (lane == 0 && row < n_rowmax) rowmax[row] = 0.f;
   }
 }
 
@@ -79,8 +89,7 @@ template <typename In>
 static int launch_frame_t(const PlanImpl& p, const In* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
                           int n_clips, int64_t n_rows, int64_t n_rows_alloc, void* d_xhi, void* d_xlo, float* d_rowmax,
                           cudaStream_t st) {
-  const int64_t total = n_rows_alloc * (p.kp / 4);
-  int64_t blocks = ceil_div(total, 256);
+  int64_t blocks = ceil_div(n_rows_alloc, 8);
   const int64_t cap = (int64_t)p.sm_count * 16;
   if (blocks > cap) blocks = cap;
   const int64_t n_rowmax = round_up(n_rows, 128);

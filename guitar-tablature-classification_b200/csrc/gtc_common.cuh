@@ -32,6 +32,7 @@ inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 int sm_count_of_current_device();
 int patch_max_ctas();
+int patch_ctas_per_sm();
 
 // index of the clip owning global item `g`:  largest c with off[c] <= g   (off has n+1 monotone entries)
 __device__ __forceinline__ int find_clip(const int64_t* __restrict__ off, int n, int64_t g) {

@@ -67,6 +67,8 @@ constexpr int kPreFast = (96 * 16) / kPatchThreads + 1;   // prefetch registers 
 
 // T_IN > 0: combined-coefficient fast path (OW % 4 == 0).  T_IN == 0: generic gather path, any size.
 template <int T_IN>
+// (capping T_IN == 5 at 64 registers so that a CTA fits beside the 160-register GEMM CTA was measured: the spills cost
+// 10 % of the store bandwidth -- 0.94 instead of 1.05 x the copy peak -- and the co-resident overlap did not pay for it)
 __global__ void __launch_bounds__(kPatchThreads, T_IN == 5 ? 4 : 2)
 patch_kernel(const PatchParams p) {
   extern __shared__ __align__(16) float smem[];
@@ -274,6 +276,8 @@ extern "C" int gtc_patches(const float* d_db, const int64_t* d_index, int64_t n,
     int per_sm = 1;
     GTC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
+    // measured on B200 (scripts/patch_cta_sweep.py): 2 CTAs/SM stream 7.08 TB/s, 4 CTAs/SM 6.88 TB/s, 1 CTA/SM 6.11 TB/s
+    if (per_sm > patch_ctas_per_sm()) per_sm = patch_ctas_per_sm();
     int64_t grid = (int64_t)sms * per_sm;
     const int64_t items = n * parts;
     if (grid > items) grid = items;

@@ -78,6 +78,11 @@ class CqtPlan:
         except Exception:
             pass
 
+    def workspace_bytes(self, n_seg: int, n_clips: int) -> int:
+        need = C.c_size_t()
+        _lib.check(_lib.load().gtc_cqt_workspace_bytes(self._h, n_seg, n_clips, C.byref(need)), "gtc_cqt_workspace_bytes")
+        return int(need.value)
+
     def workspace(self, n_seg: int, n_clips: int) -> torch.Tensor:
         need = C.c_size_t()
         _lib.check(_lib.load().gtc_cqt_workspace_bytes(self._h, n_seg, n_clips, C.byref(need)), "gtc_cqt_workspace_bytes")

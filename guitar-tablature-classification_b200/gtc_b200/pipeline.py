@@ -63,7 +63,7 @@ class _Chunk:
 class FrontEnd:
     def __init__(self, recipe: CqtRecipe = CqtRecipe(), device: Optional[int] = None, engine: Optional[int] = None,
                  patch_mode: int = _lib.GTC_PATCH_VIT, img_size=(224, 224), chunk_segments: int = 16384,
-                 patch_batch: int = 4096, overlap: bool = False, gemm_ctas: int = 64,
+                 patch_batch: int = 16384, overlap: bool = False, gemm_ctas: int = 64,
                  patch_ctas_per_sm: int = 4):
         """``overlap=True`` runs each chunk's patch kernel beside the next chunk's GEMM on disjoint SMs.  Measured on
         B200 (profiles/r01_overlap_sweep.md) it is SLOWER than running them back to back: the patch kernel needs all
@@ -84,24 +84,42 @@ class FrontEnd:
                 # the patch CTAs must not back-fill the SMs the persistent GEMM runs on (see run())
                 ops.set_option(_lib.GTC_OPT_PATCH_MAX_CTAS, (self.plan.sm_count - self.gemm_ctas) * int(patch_ctas_per_sm))
         with torch.cuda.device(self.device):
-            self.s_copy, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            self.s_copy, self.s_out, self.s_pre = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
             self.s_comp = torch.cuda.Stream(priority=-1)              # GEMM path: scheduled ahead of pending patch CTAs
             self.s_patch = torch.cuda.Stream(priority=0)
         self._bufs = {}
+        self.patch_events = None       # set to a list to collect (start_event, end_event, n_segments) of every patch launch
 
     # ------------------------------------------------------------------ host-side planning (integer arithmetic only)
-    def plan_chunks(self, inp: ShardInputs) -> List[_Chunk]:
+    def plan_chunks(self, inp: ShardInputs, ramp: bool = False) -> List[_Chunk]:
+        """Cut the shard into chunks of whole clips, at most ``chunk_segments`` segments each.  ``ramp=True`` (the host-input
+        path) makes the first chunks small (1/8, 1/4, 1/2 of the limit) and the last ones small again, so the un-overlapped
+        head (first host->device copy) and tail (last device->host copy) of the three-stream pipeline shrink 8-fold."""
         r = self.recipe
         lens = np.asarray(inp.clip_lens, dtype=np.int64)
         nseg = ops.segment_counts(lens, self.plan.seg_len, self.plan.seg_hop)
         clip_off = np.concatenate([[0], np.cumsum(lens)])
         seg_off = np.concatenate([[0], np.cumsum(nseg)])
-        chunks, c0 = [], 0
         n_clips = len(lens)
+        total = int(seg_off[-1])
+        full = self.chunk_segments
+        sizes = []
+        if ramp and total > 3 * full:
+            head, tail = [full // 8, full // 4, full // 2], [full // 2, full // 8]
+            body = total - sum(head) - sum(tail)
+            n_body = -(-body // full)
+            sizes = head + [-(-body // n_body)] * n_body + tail
+        marks = np.cumsum(sizes) if sizes else None              # target cumulative segment counts of the chunk ends
+        chunks, c0, k = [], 0, 0
         while c0 < n_clips:
             c1 = c0 + 1
-            while c1 < n_clips and seg_off[c1 + 1] - seg_off[c0] <= self.chunk_segments:
-                c1 += 1
+            if marks is not None and k < len(marks) - 1:
+                while c1 < n_clips and seg_off[c1 + 1] <= marks[k] and seg_off[c1 + 1] - seg_off[c0] <= full:
+                    c1 += 1
+            else:
+                while c1 < n_clips and seg_off[c1 + 1] - seg_off[c0] <= full:
+                    c1 += 1
+            k += 1
             ch = _Chunk(c0, c1, int(clip_off[c0]), int(clip_off[c1]), int(seg_off[c0]), int(seg_off[c1]),
                         int(inp.evt_off[c0]), int(inp.evt_off[c1]))
             assert ch.g1 - ch.g0 <= max(self.chunk_segments, int(nseg[c0]))
@@ -134,7 +152,7 @@ class FrontEnd:
         """Process one shard.  ``consumer(patches, tabs_batch, first_segment_index)`` is called on the compute stream
         for every patch batch (the training engine's input); without it patches are produced into a ring and dropped."""
         plan, dev = self.plan, self.dev
-        chunks = self.plan_chunks(inp) if chunks is None else chunks
+        chunks = self.plan_chunks(inp, ramp=not device_inputs) if chunks is None else chunks
         n_seg = chunks[-1].g1 if chunks else 0
         out = ShardOutputs(n_seg=n_seg, seconds_of_audio=float(np.sum(inp.clip_lens)) / float(inp.sr))
         nb, T = plan.n_bins, plan.n_frames
@@ -150,9 +168,11 @@ class FrontEnd:
         max_seg = max((c.g1 - c.g0 for c in chunks), default=1)
         max_evt = max((c.e1 - c.e0 for c in chunks), default=1)
         max_clips = max((c.c1 - c.c0 for c in chunks), default=1)
-        ws = plan.workspace(max_seg, max_clips)
+        ws_bytes = plan.workspace_bytes(max_seg, max_clips)
+        ws2 = [self._buf(f"ws{j}", (ws_bytes,), torch.uint8) for j in range(2)]      # framed operands, double-buffered
+        ev_pre = [None, None]
+        ev_ws = [None, None]                                                          # GEMM that last read ws2[b]
         pb = min(self.patch_batch, max(1, max_seg))
-        ev_done = [None, None]
         ev_free = [[], []]
         # all chunk metadata (offsets, label times) goes up in one copy from pinned memory
         meta_np = np.concatenate([np.concatenate([c.clip_off, c.seg_off, c.evt_off]) for c in chunks]).astype(np.int64) \
@@ -165,7 +185,9 @@ class FrontEnd:
         d_meta_all = self._buf("meta_dev", (meta_np.size,), torch.int64)
         d_time_all = self._buf("time_dev", (max(1, time_np.size),), torch.float64)
         with torch.cuda.device(self.device):
+            stats.zero_()
             self.s_copy.wait_stream(torch.cuda.current_stream())
+            self.s_pre.wait_stream(torch.cuda.current_stream())
             self.s_comp.wait_stream(torch.cuda.current_stream())
             self.s_out.wait_stream(torch.cuda.current_stream())
             self.s_patch.wait_stream(torch.cuda.current_stream())
@@ -174,8 +196,6 @@ class FrontEnd:
                 d_time_all.copy_(h_time, non_blocking=True)
                 if not device_inputs:
                     out.h2d_bytes += meta_np.nbytes + time_np.nbytes
-            with torch.cuda.stream(self.s_comp):
-                stats.zero_()
             def emit(job, gate, s_p):
                 jb, jch, j_db, j_tabs, _ = job
                 jng = jch.g1 - jch.g0
@@ -184,7 +204,13 @@ class FrontEnd:
                     for j, p0 in enumerate(range(0, jng, pb)):
                         p1 = min(jng, p0 + pb)
                         ring = self._buf(f"patch{j & 1}", (pb, 3) + self.img_size, torch.float32)[: p1 - p0]
+                        if self.patch_events is not None:
+                            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            t0.record(s_p)
                         ops.patches(j_db[p0:p1], img_size=self.img_size, mode=self.patch_mode, out=ring)
+                        if self.patch_events is not None:
+                            t1.record(s_p)
+                            self.patch_events.append((t0, t1, p1 - p0))
                         out.launches += 1
                         if consumer is not None:
                             consumer(ring, j_tabs[p0:p1], jch.g0 + p0)
@@ -202,8 +228,8 @@ class FrontEnd:
                 d_time = d_time_all[ch.g0:ch.g1]
                 # ---- stage inputs
                 with torch.cuda.stream(self.s_copy):
-                    if ev_done[b] is not None:
-                        self.s_copy.wait_event(ev_done[b])            # buffers of chunk k-2 are free again
+                    if ev_pre[b] is not None:
+                        self.s_copy.wait_event(ev_pre[b])             # chunk k-2's framing / label kernels have read audio{b}, ev{b}
                     if device_inputs:
                         d_audio = inp.audio[ch.s0:ch.s1]
                         d_ev = inp.events[:, ch.e0:ch.e1]
@@ -216,28 +242,39 @@ class FrontEnd:
                             d_evb[j, :ne].copy_(inp.events[j, ch.e0:ch.e1], non_blocking=True)
                         d_on, d_du, d_pi = d_evb[0, :ne], d_evb[1, :ne], d_evb[2, :ne]
                         out.h2d_bytes += ns * inp.audio.element_size() + ne * 24
+                    ev_h2d = torch.cuda.Event()
+                    ev_h2d.record(self.s_copy)
+                with torch.cuda.stream(self.s_pre):
+                    self.s_pre.wait_event(ev_h2d)
+                    d_clip_off, d_seg_off, d_evt_off = d_meta[: nc + 1], d_meta[nc + 1: 2 * nc + 2], d_meta[2 * nc + 2:]
+                    d_db = out.db[ch.g0:ch.g1] if not host_out else self._buf(f"db{b}", (max_seg, nb, T), torch.float32)[:ng]
+                    d_tabs = out.tabs[ch.g0:ch.g1] if not host_out else self._buf(f"tabs{b}", (max_seg, 6, 19), torch.int8)[:ng]
+                    # ---- framing (HBM-bound) and label rasterisation (latency-bound) run on their own stream, so they
+                    #      execute under the previous chunk's tensor-core GEMM / patch stores instead of in front of this
+                    #      chunk's GEMM, and never hold up the next host->device copy
+                    if ng:
+                        if ev_ws[b] is not None:
+                            self.s_pre.wait_event(ev_ws[b])           # the GEMM of chunk k-2 has consumed ws2[b]
+                        for e in ev_free[b]:
+                            self.s_pre.wait_event(e)                  # chunk k-2's patches / D2H released tabs{b}
+                        plan.frame(d_audio, d_clip_off, d_seg_off, ng, ws2[b])
+                        ops.rasterize_tabs(d_on, d_du, d_pi, d_evt_off, d_time, d_seg_off, out=d_tabs, stats=stats)
+                        out.launches += 2
                     ev_in = torch.cuda.Event()
-                    ev_in.record(self.s_copy)
-                d_clip_off, d_seg_off, d_evt_off = d_meta[: nc + 1], d_meta[nc + 1: 2 * nc + 2], d_meta[2 * nc + 2:]
-                # ---- CQT (frame + tcgen05 GEMM + dB finish) and labels
+                    ev_in.record(self.s_pre)
+                ev_pre[b] = ev_in
+                # ---- tensor-core contraction + dB finish
                 with torch.cuda.stream(self.s_comp):
                     self.s_comp.wait_event(ev_in)
                     for e in ev_free[b]:
-                        self.s_comp.wait_event(e)                     # chunk k-2's patches / D2H released db{b}, tabs{b}
-                    d_db = out.db[ch.g0:ch.g1] if not host_out else self._buf(f"db{b}", (max_seg, nb, T), torch.float32)[:ng]
-                    d_tabs = out.tabs[ch.g0:ch.g1] if not host_out else self._buf(f"tabs{b}", (max_seg, 6, 19), torch.int8)[:ng]
-                    ev_g = None
+                        self.s_comp.wait_event(e)                     # chunk k-2's patches / D2H released db{b}
+                    ev_g = ev_in if self.overlap else None
                     if ng:
-                        plan.frame(d_audio, d_clip_off, d_seg_off, ng, ws)
-                        if self.overlap:
-                            ev_g = torch.cuda.Event()                 # "the GEMM of chunk k is the next thing on s_comp"
-                            ev_g.record(self.s_comp)
-                        plan.contract_db(d_clip_off, d_seg_off, ng, d_db, ws)
-                        ops.rasterize_tabs(d_on, d_du, d_pi, d_evt_off, d_time, d_seg_off, out=d_tabs, stats=stats)
-                        out.launches += 4
+                        plan.contract_db(d_clip_off, d_seg_off, ng, d_db, ws2[b])
+                        out.launches += 2
                     ev_k = torch.cuda.Event()
                     ev_k.record(self.s_comp)
-                ev_done[b] = ev_k                                     # audio{b} / ev{b} may be overwritten after this
+                ev_ws[b] = ev_k
                 ev_free[b] = []
                 # ---- patches.  Overlap mode: the store-bound patch kernel of chunk k-1 is released on its own
                 #      (low-priority) stream at the moment the tensor-core GEMM of chunk k becomes runnable on the
@@ -270,6 +307,7 @@ class FrontEnd:
             torch.cuda.current_stream().wait_stream(self.s_out)
             torch.cuda.current_stream().wait_stream(self.s_comp)
             torch.cuda.current_stream().wait_stream(self.s_copy)
+            torch.cuda.current_stream().wait_stream(self.s_pre)
             torch.cuda.current_stream().wait_stream(self.s_patch)
         self._last_stats = (stats, self._bufs.get(("stats_host", True)) if host_out else None)
         return out

@@ -65,7 +65,7 @@ def stream_corpus(n_clips: int, clip_seconds: float, rank: int = 0, world_size: 
     n_samples = int(sr * clip_seconds)
     mine = shard.partition_round_robin(n_clips, rank, world_size)
     patch_mode = _lib.GTC_PATCH_VIT if mode == "vit" else _lib.GTC_PATCH_CNN
-    ring = max(batch_size, (4096 // batch_size) * batch_size)
+    ring = max(batch_size, (16384 // batch_size) * batch_size)
     fe = FrontEnd(recipe, device=dev_index, patch_mode=patch_mode, patch_batch=ring)
     rep = StreamReport(label_stats=np.zeros(3, dtype=np.int64))
 

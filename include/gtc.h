@@ -102,6 +102,7 @@ int gtc_cqt_contract_db(const gtc_plan* plan, const int64_t* d_clip_off, const i
                         float power, float amin, float top_db, float cut_db, float floor_db, gtc_stream_t stream);
 /* process-wide tunables */
 #define GTC_OPT_PATCH_MAX_CTAS 16  /* grid limit of the patch kernel (0 = SMs x resident CTAs) */
+#define GTC_OPT_PATCH_CTAS_PER_SM 17 /* resident patch CTAs per SM (default 2: measured fastest on B200; 0 restores the default) */
 int gtc_set_option(int option, int value);
 
 /* Same contraction, complex output before |.|: d_out_c [n_seg, n_bins, n_frames, 2] fp32 (== librosa.cqt). */
