@@ -247,8 +247,12 @@ def run_cuda_arm(args):
     audio_host.copy_(audio_dev if args.host_audio == "f32" else pcm_dev)
     del pcm_dev
     lens = np.full(n_clips, n, dtype=np.int64)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        __import__("gtc_b200.ops", fromlist=["set_option"]).set_option(int(k), int(v))
     fe = FrontEnd(recipe, device=local_rank, engine=args.engine, chunk_segments=args.chunk_segments, patch_batch=args.patch_batch,
-                  overlap=args.overlap, gemm_ctas=args.gemm_ctas, patch_ctas_per_sm=args.patch_ctas_per_sm)
+                  overlap=args.overlap, gemm_ctas=args.gemm_ctas, patch_ctas_per_sm=args.patch_ctas_per_sm,
+                  coresident=args.coresident, wave_aware=not args.no_wave_aware)
     inp_dev = ShardInputs(audio_dev, lens, events_dev, evt_off, sr=SR)
     inp_host = ShardInputs(audio_host, lens, events_host, evt_off, sr=SR)
     chunks = fe.plan_chunks(inp_dev)
@@ -278,6 +282,7 @@ def run_cuda_arm(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         fe.patch_events = [] if device_inputs else None      # per-launch CUDA events on the launching stream, timed region only
+        fe.gemm_events = [] if device_inputs else None
         e0.record()
         out = None
         for _ in range(steps):
@@ -286,7 +291,8 @@ def run_cuda_arm(args):
         barrier()
         if device_inputs:
             timed.patch_launches = [(a.elapsed_time(b), n) for a, b, n in fe.patch_events]
-        fe.patch_events = None
+            timed.gemm_launches = [(a.elapsed_time(b), n) for a, b, n in fe.gemm_events]
+        fe.patch_events = fe.gemm_events = None
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -355,7 +361,11 @@ def run_cuda_arm(args):
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                              "launch_ms": live_ms, "segments_per_launch": live_seg, "launches_timed": len(live),
                              "how": "mean of per-launch CUDA events on the launching stream inside the timed steps (next chunk's framing/label kernels run beside it)",
+                             "per_launch_ms": [round(t, 3) for t, _ in live], "per_launch_segments": [n for _, n in live],
                              "isolated": {"achieved": isolated, "frac": isolated / peak_hbm, "launch_ms": patch_ms, "segments_per_launch": pb}},
+                "gemm_live": {"kernel": "gemm_tc_kernel + finish_db_kernel", "launch_ms": float(np.mean([t for t, _ in getattr(timed, "gemm_launches", [(0.0, 0)])])),
+                              "segments_per_launch": float(np.mean([n for _, n in getattr(timed, "gemm_launches", [(0.0, 0)])])),
+                              "how": "per-launch CUDA events on the GEMM stream inside the timed steps"},
                 "path_roofline": {"algorithmic_bytes_per_s_audio": ALGO_BYTES_PER_S_AUDIO,
                                   "frac_of_hbm_peak": (value / world) * ALGO_BYTES_PER_S_AUDIO / (peak_hbm * 1e9)},
                 "cpu_baseline": cpu_baseline,
@@ -373,12 +383,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=N_CLIPS)
-    ap.add_argument("--chunk-segments", type=int, default=16384)
-    ap.add_argument("--patch-batch", type=int, default=16384, help="segments per patch launch (one launch per chunk measured fastest)")
+    ap.add_argument("--chunk-segments", type=int, default=19200, help="upper limit of segments per chunk; the planner ends chunks where the GEMM tile waves are full")
+    ap.add_argument("--patch-batch", type=int, default=19200, help="segments per patch launch (one launch per chunk measured fastest)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ramp", action="store_true", help="e2e arm: equal chunks instead of the ramped first/last chunks")
     ap.add_argument("--host-audio", default="pcm16", choices=["pcm16", "f32"], help="sample type of the pinned host audio of the e2e arm")
     ap.add_argument("--engine", type=int, default=None, help="GEMM engine: 0 tcgen05 3xTF32, 1 SIMT fp32, 2 tcgen05 fp16x2 (default: library default)")
+    ap.add_argument("--coresident", action="store_true", help="experiment: patch kernels on their own stream under the next chunk GEMM (needs -DTC_MAXNREG=152; slower, see profiles/r01j_coresident.md)")
+    ap.add_argument("--no-wave-aware", action="store_true", help="plain greedy chunks (largest that fit) instead of full GEMM tile waves")
+    ap.add_argument("--opt", action="append", default=[], help="library option id=value (gtc_set_option), for experiments")
     ap.add_argument("--overlap", action="store_true", help="run each chunk's patch kernel beside the next chunk's GEMM (slower on B200, see profiles/)")
     ap.add_argument("--patch-ctas-per-sm", type=int, default=4, help="0 = do not limit the patch grid while overlapping")
     ap.add_argument("--gemm-ctas", type=int, default=56, help="SMs given to the persistent tcgen05 GEMM while patches overlap")

@@ -28,6 +28,9 @@ constexpr uint32_t STAGE_BYTES = 2 * X_TILE_BYTES + 2 * OP_TILE_BYTES;   // 96 K
 constexpr uint32_t TC_SMEM_BYTES = TSTAGES * STAGE_BYTES + 1024 /*align slack*/;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+#ifndef TC_MAXNREG
+#define TC_MAXNREG 168
+#endif
 
 struct TcParams {
   int nc;                // operator rows per tile
@@ -137,8 +140,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&r)[8]) {
 // in fp32 (round-to-nearest) by the epilogue warps while the next split is already being multiplied.
 // kHalf: operands are fp16 hi/lo pairs (kind::f16, 64 elements per 128-byte k-block, 16 per MMA) instead of tf32 pairs
 // (kind::tf32, 32 per k-block, 8 per MMA); in bytes the tiles, the swizzle and the +32 B k-step are identical.
+//
+// Register cap (TC_MAXNREG, default 168 = what ptxas picks for 320 threads/SM, no spills).  Building with
+// -DTC_MAXNREG=152 gives 48 640 registers per CTA, so that one 224-thread x 72-register patch CTA (patches.cu) fits on
+// the SM beside this one (FrontEnd(coresident=True)).  Measured on B200 (profiles/r01j_coresident.md): co-running the
+// two kernels is SLOWER than back to back -- both live on L2 bandwidth (operator tiles re-read by every M tile here,
+// 7 TB/s of stores there): GEMM+finish 0.36 -> 0.94 ms, patch launch 1.29 -> 1.93 ms per chunk.
 template <int NC, bool kComplex, bool kHalf>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __maxnreg__(TC_MAXNREG)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo,
                const TcParams prm) {

@@ -12,6 +12,7 @@
 //     pass T -> OW is fused with the store: every thread owns one float4 column group and keeps its 4 x T combined
 //     interpolation coefficients in registers, so a row costs 2 LDS.128 + 4T FFMA and three 16-byte streaming
 //     stores (one per channel); a warp writes 512 contiguous bytes per store instruction.
+#include <stdlib.h>
 #include "gtc_common.cuh"
 
 namespace gtc {
@@ -271,18 +272,32 @@ extern "C" int gtc_patches(const float* d_db, const int64_t* d_index, int64_t n,
   const int tp = (n_frames + 3) & ~3;
   const size_t smem = sizeof(float) * (((size_t)n_bins * n_frames + 3) / 4 * 4 + (size_t)rpp * tp + (size_t)out_h * 8);
   GTC_REQUIRE(smem <= 200 * 1024, GTC_E_UNSUP, "gtc_patches: %zu bytes of shared memory needed", smem);
+  // Residency is pinned through the shared-memory request.  The CTAs are persistent (ticket loop), so where they land at
+  // launch is where they stay: with the small natural footprint (11 KB, 72 registers) four fit on an SM, and when another
+  // kernel still holds some SMs at launch time (the label / framing kernels of the next chunk, a consumer's kernels) the
+  // 2 x 148 CTAs pile up 3-4 deep on the free SMs and leave the others empty for the whole launch -- measured on B200:
+  // 4.5 instead of 7.2 TB/s, per launch and depending on the chunk size (profiles/r01j_patch_residency.md).  Asking for
+  // 228 KB / k per CTA makes k CTAs fill an SM, so the grid of k x 148 can only be placed evenly.
+  const int want_per_sm = patch_ctas_per_sm();
+  size_t smem_req = smem;
+  {
+    const size_t even = (size_t)(228 * 1024) / (size_t)want_per_sm - 1024 - 256;    // 1 KB per CTA is reserved by the system
+    if (even > smem_req) smem_req = even;
+  }
   auto launch = [&](auto kern) -> int {
-    if (smem > 48 * 1024) GTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const char* pin = getenv("GTC_PATCH_NO_PIN");                // experiment switch: natural footprint
+    const size_t sm_bytes = pin ? smem : smem_req;
+    if (sm_bytes > 48 * 1024) GTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_bytes));
     int per_sm = 1;
-    GTC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    GTC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, sm_bytes));
     if (per_sm < 1) per_sm = 1;
     // measured on B200 (scripts/patch_cta_sweep.py): 2 CTAs/SM stream 7.08 TB/s, 4 CTAs/SM 6.88 TB/s, 1 CTA/SM 6.11 TB/s
-    if (per_sm > patch_ctas_per_sm()) per_sm = patch_ctas_per_sm();
+    if (per_sm > want_per_sm) per_sm = want_per_sm;
     int64_t grid = (int64_t)sms * per_sm;
     const int64_t items = n * parts;
     if (grid > items) grid = items;
     if (patch_max_ctas() > 0 && grid > patch_max_ctas()) grid = patch_max_ctas();
-    kern<<<(unsigned)grid, threads, smem, st>>>(p);
+    kern<<<(unsigned)grid, threads, sm_bytes, st>>>(p);
     GTC_CUDA_CHECK(cudaGetLastError());
     return GTC_OK;
   };

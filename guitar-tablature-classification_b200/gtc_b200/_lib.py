@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgtc.so")
+LIB_PATH = os.environ.get("GTC_LIB_PATH") or os.path.join(_HERE, "libgtc.so")   # the override is for A/B kernel experiments
 
 GTC_GEMM_TCGEN05_3XTF32 = 0
 GTC_GEMM_SIMT_FP32 = 1

@@ -63,6 +63,22 @@ class CqtPlan:
         self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
         self._ws: Optional[torch.Tensor] = None
 
+    @property
+    def parts(self) -> int:
+        """Audio rows per segment (P): a segment of seg_len = P * seg_hop samples is P consecutive operand rows."""
+        return int(_lib.load().gtc_cqt_plan_parts(self._h))
+
+    def gemm_wave_efficiency(self, n_seg: int, n_clips: int) -> float:
+        """Fraction of the persistent tcgen05 GEMM's last wave that is filled for a chunk of ``n_seg`` segments in
+        ``n_clips`` clips: tiles = ceil(rows / 128) x ceil(n_out / tile width) are dealt round-robin to one CTA per SM
+        (cqt_gemm_tc.cu), so a chunk of 3.4 waves costs as much as one of 4.0.  Used by the chunk planner."""
+        rows = int(n_seg) + int(n_clips) * (self.parts - 1)
+        n_out = 2 * self.n_bins * self.n_frames
+        nc = next((w for w in (256, 240, 192, 128, 64) if n_out % w == 0), 256)
+        tiles = -(-rows // 128) * -(-n_out // nc)
+        waves = -(-tiles // self.sm_count)
+        return tiles / float(waves * self.sm_count) if tiles else 1.0
+
     def configure(self, option: int, value: int) -> None:
         """Tuning knobs (GTC_OPT_TC_KSPLIT, GTC_OPT_GEMM_MAX_CTAS)."""
         _lib.check(_lib.load().gtc_cqt_plan_configure(self._h, int(option), int(value)), "gtc_cqt_plan_configure")

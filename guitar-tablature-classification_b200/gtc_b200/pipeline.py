@@ -62,12 +62,16 @@ class _Chunk:
 
 class FrontEnd:
     def __init__(self, recipe: CqtRecipe = CqtRecipe(), device: Optional[int] = None, engine: Optional[int] = None,
-                 patch_mode: int = _lib.GTC_PATCH_VIT, img_size=(224, 224), chunk_segments: int = 16384,
-                 patch_batch: int = 16384, overlap: bool = False, gemm_ctas: int = 64,
-                 patch_ctas_per_sm: int = 4):
-        """``overlap=True`` runs each chunk's patch kernel beside the next chunk's GEMM on disjoint SMs.  Measured on
-        B200 (profiles/r01_overlap_sweep.md) it is SLOWER than running them back to back: the patch kernel needs all
-        148 SMs to saturate HBM stores, so the default keeps the two kernels sequential."""
+                 patch_mode: int = _lib.GTC_PATCH_VIT, img_size=(224, 224), chunk_segments: int = 19200,
+                 patch_batch: int = 19200, overlap: bool = False, gemm_ctas: int = 64,
+                 patch_ctas_per_sm: int = 4, coresident: bool = False, wave_aware: bool = True):
+        """``coresident=True``: the patch kernels run on their own lower-priority stream, gated only by their chunk's dB
+        features, while the GEMM stream goes on with the next chunks, so that (with libgtc built -DTC_MAXNREG=152) one
+        patch CTA per SM runs beside the GEMM CTA.  ``overlap=True`` is the older experiment with the two kernels on
+        DISJOINT SMs.  Both were measured on B200 and are SLOWER than running the kernels back to back
+        (profiles/r01j_coresident.md, profiles/r01_overlap_sweep.md): the GEMM re-reads its operator tiles from L2 for
+        every M tile and the patch kernel pushes 7 TB/s of stores through the same L2, so they do not hide each other.
+        The default keeps them sequential."""
         self.recipe = recipe
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.dev = torch.device(f"cuda:{self.device}")
@@ -77,6 +81,8 @@ class FrontEnd:
         self.chunk_segments = int(chunk_segments)
         self.patch_batch = int(patch_batch)
         self.overlap = bool(overlap)
+        self.coresident = bool(coresident) and not self.overlap
+        self.wave_aware = bool(wave_aware)
         self.gemm_ctas = int(gemm_ctas) if self.overlap else 0
         if self.gemm_ctas > 0:
             self.plan.configure(_lib.GTC_OPT_GEMM_MAX_CTAS, self.gemm_ctas)
@@ -89,6 +95,8 @@ class FrontEnd:
             self.s_patch = torch.cuda.Stream(priority=0)
         self._bufs = {}
         self.patch_events = None       # set to a list to collect (start_event, end_event, n_segments) of every patch launch
+        self.gemm_events = None        # same for every GEMM + dB-finish pair
+        self.trace = None              # set to a list to collect (label, stream name, event) marks: scripts/timeline.py
 
     # ------------------------------------------------------------------ host-side planning (integer arithmetic only)
     def plan_chunks(self, inp: ShardInputs, ramp: bool = False) -> List[_Chunk]:
@@ -119,6 +127,11 @@ class FrontEnd:
             else:
                 while c1 < n_clips and seg_off[c1 + 1] - seg_off[c0] <= full:
                     c1 += 1
+            if self.wave_aware and c1 < n_clips and c1 - c0 > 4:
+                # the largest chunk is not the cheapest: end it where the GEMM's last wave of tiles is full
+                lo = c0 + max(1, int(0.8 * (c1 - c0)))
+                c1 = max(range(lo, c1 + 1),
+                         key=lambda c: (round(self.plan.gemm_wave_efficiency(int(seg_off[c] - seg_off[c0]), c - c0), 2), c))
             k += 1
             ch = _Chunk(c0, c1, int(clip_off[c0]), int(clip_off[c1]), int(seg_off[c0]), int(seg_off[c1]),
                         int(inp.evt_off[c0]), int(inp.evt_off[c1]))
@@ -136,6 +149,12 @@ class FrontEnd:
             chunks.append(ch)
             c0 = c1
         return chunks
+
+    def _mark(self, label, stream, name):
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            self.trace.append((label, name, e))
 
     def _buf(self, name, shape, dtype, pinned=False):
         key = (name, pinned)
@@ -207,7 +226,9 @@ class FrontEnd:
                         if self.patch_events is not None:
                             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                             t0.record(s_p)
+                        self._mark(f"patch{jch.c0}<", s_p, "patch")
                         ops.patches(j_db[p0:p1], img_size=self.img_size, mode=self.patch_mode, out=ring)
+                        self._mark(f"patch{jch.c0}>", s_p, "patch")
                         if self.patch_events is not None:
                             t1.record(s_p)
                             self.patch_events.append((t0, t1, p1 - p0))
@@ -230,6 +251,7 @@ class FrontEnd:
                 with torch.cuda.stream(self.s_copy):
                     if ev_pre[b] is not None:
                         self.s_copy.wait_event(ev_pre[b])             # chunk k-2's framing / label kernels have read audio{b}, ev{b}
+                    self._mark(f"h2d{k}<", self.s_copy, "copy")
                     if device_inputs:
                         d_audio = inp.audio[ch.s0:ch.s1]
                         d_ev = inp.events[:, ch.e0:ch.e1]
@@ -242,6 +264,7 @@ class FrontEnd:
                             d_evb[j, :ne].copy_(inp.events[j, ch.e0:ch.e1], non_blocking=True)
                         d_on, d_du, d_pi = d_evb[0, :ne], d_evb[1, :ne], d_evb[2, :ne]
                         out.h2d_bytes += ns * inp.audio.element_size() + ne * 24
+                    self._mark(f"h2d{k}>", self.s_copy, "copy")
                     ev_h2d = torch.cuda.Event()
                     ev_h2d.record(self.s_copy)
                 with torch.cuda.stream(self.s_pre):
@@ -249,16 +272,21 @@ class FrontEnd:
                     d_clip_off, d_seg_off, d_evt_off = d_meta[: nc + 1], d_meta[nc + 1: 2 * nc + 2], d_meta[2 * nc + 2:]
                     d_db = out.db[ch.g0:ch.g1] if not host_out else self._buf(f"db{b}", (max_seg, nb, T), torch.float32)[:ng]
                     d_tabs = out.tabs[ch.g0:ch.g1] if not host_out else self._buf(f"tabs{b}", (max_seg, 6, 19), torch.int8)[:ng]
-                    # ---- framing (HBM-bound) and label rasterisation (latency-bound) run on their own stream, so they
-                    #      execute under the previous chunk's tensor-core GEMM / patch stores instead of in front of this
-                    #      chunk's GEMM, and never hold up the next host->device copy
+                    # ---- framing (HBM-bound) and label rasterisation (latency-bound) run on their own stream and start
+                    #      when chunk k-2's patches are done, i.e. together with chunk k-1's GEMM.  Measured on B200
+                    #      (profiles/r01j_timelines.md): beside the GEMM the framing kernel costs 0.035 ms per chunk;
+                    #      released earlier (right after the GEMM of chunk k-2, under the patch stores) it slows the
+                    #      store stream by 0.09 ms per chunk and more, so the patch-completion wait below stays.
                     if ng:
                         if ev_ws[b] is not None:
                             self.s_pre.wait_event(ev_ws[b])           # the GEMM of chunk k-2 has consumed ws2[b]
                         for e in ev_free[b]:
                             self.s_pre.wait_event(e)                  # chunk k-2's patches / D2H released tabs{b}
+                        self._mark(f"frame{k}<", self.s_pre, "pre")
                         plan.frame(d_audio, d_clip_off, d_seg_off, ng, ws2[b])
+                        self._mark(f"frame{k}>", self.s_pre, "pre")
                         ops.rasterize_tabs(d_on, d_du, d_pi, d_evt_off, d_time, d_seg_off, out=d_tabs, stats=stats)
+                        self._mark(f"labels{k}>", self.s_pre, "pre")
                         out.launches += 2
                     ev_in = torch.cuda.Event()
                     ev_in.record(self.s_pre)
@@ -270,7 +298,15 @@ class FrontEnd:
                         self.s_comp.wait_event(e)                     # chunk k-2's patches / D2H released db{b}
                     ev_g = ev_in if self.overlap else None
                     if ng:
+                        if self.gemm_events is not None:
+                            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            t0.record(self.s_comp)
+                        self._mark(f"gemm{k}<", self.s_comp, "comp")
                         plan.contract_db(d_clip_off, d_seg_off, ng, d_db, ws2[b])
+                        self._mark(f"gemm{k}>", self.s_comp, "comp")
+                        if self.gemm_events is not None:
+                            t1.record(self.s_comp)
+                            self.gemm_events.append((t0, t1, ng))
                         out.launches += 2
                     ev_k = torch.cuda.Event()
                     ev_k.record(self.s_comp)
@@ -284,13 +320,15 @@ class FrontEnd:
                         emit(pending, ev_g if ev_g is not None else ev_k, self.s_patch)
                     pending = (b, ch, d_db, d_tabs, ev_k) if ng else None
                 elif emit_patches and ng:
-                    emit((b, ch, d_db, d_tabs, ev_k), ev_k, self.s_comp)
+                    emit((b, ch, d_db, d_tabs, ev_k), ev_k, self.s_patch if self.coresident else self.s_comp)
                 # ---- results back to the host
                 if host_out:
                     with torch.cuda.stream(self.s_out):
                         self.s_out.wait_event(ev_k)
+                        self._mark(f"d2h{k}<", self.s_out, "out")
                         out.db[ch.g0:ch.g1].copy_(d_db, non_blocking=True)
                         out.tabs[ch.g0:ch.g1].copy_(d_tabs, non_blocking=True)
+                        self._mark(f"d2h{k}>", self.s_out, "out")
                         out.d2h_bytes += ng * (nb * T * 4 + 114)
                         ev_o = torch.cuda.Event()
                         ev_o.record(self.s_out)

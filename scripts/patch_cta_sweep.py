@@ -10,8 +10,13 @@ n = 8192
 db = (torch.rand((n, 96, 5), device=dev) * 120 - 120)
 out = torch.empty((n, 3, 224, 224), device=dev)
 byts = n * (3 * 224 * 224 * 4 + 1920)
-for ctas in (0, 148 * 4, 148 * 3, 148 * 2, 148, 132 * 4, 120 * 4, 100 * 4):
+for ahead, ctas in [(a, c) for c in (148 * 2, 148, 148 * 3) for a in (0, 1, 0, 1)]:
     ops.set_option(16, ctas)
+    ops.set_option(17, 4)
+    try:
+        ops.set_option(18, ahead)
+    except Exception:
+        if ahead: continue
     for _ in range(3): ops.patches(db, out=out)
     torch.cuda.synchronize()
     ts = []
@@ -19,5 +24,5 @@ for ctas in (0, 148 * 4, 148 * 3, 148 * 2, 148, 132 * 4, 120 * 4, 100 * 4):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); ops.patches(db, out=out); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     ms = float(np.mean(ts))
-    print(json.dumps({"max_ctas": ctas, "ms": round(ms, 4), "GBs": round(byts / ms / 1e6, 1)}), flush=True)
-ops.set_option(16, 0)
+    print(json.dumps({"ahead": ahead, "max_ctas": ctas, "ms": round(ms, 4), "GBs": round(byts / ms / 1e6, 1)}), flush=True)
+ops.set_option(16, 0); ops.set_option(17, 0)
