@@ -151,7 +151,8 @@ class ClockSampler:
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
                0x100: "display_clock_setting"}
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period: float = 0.02):
+        self.period = period
         self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
         self._t = None
         try:
@@ -173,10 +174,10 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(self.period)
 
     def __enter__(self):
-        if self.nv is not None:
+        if self.nv is not None and self.period > 0:
             self._t = threading.Thread(target=self._loop, daemon=True)
             self._t.start()
         return self
@@ -260,12 +261,15 @@ def run_cuda_arm(args):
     seconds_per_step = n_clips * CLIP_SECONDS
     stats_vec = torch.zeros(8, dtype=torch.int64, device=dev)
 
+    # shard constants of the stats vector: staged once in pinned memory.  (`stats_vec[0] = n_clips` would be a copy from
+    # PAGEABLE host memory, which synchronises the stream first -- one hidden host sync per step.)
+    stats_head = torch.tensor([n_clips, 0, int(lens.sum())], dtype=torch.int64).pin_memory()
+
     def step(inp, device_inputs):
         out = fe.run(inp, device_inputs=device_inputs, chunks=chunks if device_inputs else chunks_host)
         # tiny per-shard stats gather (the path's only collective), jam_to_tablature.py:376-378
-        stats_vec[0] = n_clips
-        stats_vec[1] = out.n_seg
-        stats_vec[2] = int(lens.sum())
+        stats_head[1] = out.n_seg
+        stats_vec[:3].copy_(stats_head, non_blocking=True)
         stats_vec[3:6] = fe._last_stats[0]
         if world > 1:
             shard.gather_stats(stats_vec)
@@ -285,8 +289,10 @@ def run_cuda_arm(args):
         fe.gemm_events = [] if device_inputs else None
         e0.record()
         out = None
+        t_host = time.perf_counter()
         for _ in range(steps):
             out = step(inp, device_inputs)
+        timed.host_ms = 1e3 * (time.perf_counter() - t_host) / max(1, steps)     # CPU time to enqueue one step
         e1.record()
         barrier()
         if device_inputs:
@@ -298,8 +304,9 @@ def run_cuda_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), out
 
-    with ClockSampler(physical_gpu_index(local_rank)) as clocks:
+    with ClockSampler(physical_gpu_index(local_rank), period=args.clock_period) as clocks:
         ms_dev, out_dev = timed(inp_dev, True, args.steps, args.warmup)
+    host_ms_dev = timed.host_ms
     ms_e2e, out_e2e = timed(inp_host, False, args.steps, args.warmup)
 
     # dominant kernel (patch store stream) timed live, per launch, on its own stream
@@ -355,7 +362,7 @@ def run_cuda_arm(args):
                         "h2d_bytes_per_step": out_e2e.h2d_bytes, "d2h_bytes_per_step": out_e2e.d2h_bytes,
                         "host_audio": "int16 PCM (the WAV files' samples; x/32768 on the device == librosa.load)" if args.host_audio == "pcm16" else "fp32",
                         "note": "pinned host audio+events in, dB features + labels + stats back; patches stay in HBM for the engines"},
-                "gpu_launches": out_dev.launches * args.steps,
+                "gpu_launches": out_dev.launches * args.steps, "host_enqueue_ms_per_step": host_ms_dev,
                 "roofline": {"bound": "hbm", "kernel": "patch_kernel<5> (gtc_patches)", "achieved": achieved, "peak": peak_hbm,
                              "unit": "GB/s", "frac": achieved / peak_hbm, "traffic": traffic,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
@@ -391,6 +398,7 @@ def main():
     ap.add_argument("--engine", type=int, default=None, help="GEMM engine: 0 tcgen05 3xTF32, 1 SIMT fp32, 2 tcgen05 fp16x2 (default: library default)")
     ap.add_argument("--coresident", action="store_true", help="experiment: patch kernels on their own stream under the next chunk GEMM (needs -DTC_MAXNREG=152; slower, see profiles/r01j_coresident.md)")
     ap.add_argument("--no-wave-aware", action="store_true", help="plain greedy chunks (largest that fit) instead of full GEMM tile waves")
+    ap.add_argument("--clock-period", type=float, default=0.02, help="seconds between NVML clock samples during the timed region (0 = off)")
     ap.add_argument("--opt", action="append", default=[], help="library option id=value (gtc_set_option), for experiments")
     ap.add_argument("--overlap", action="store_true", help="run each chunk's patch kernel beside the next chunk's GEMM (slower on B200, see profiles/)")
     ap.add_argument("--patch-ctas-per-sm", type=int, default=4, help="0 = do not limit the patch grid while overlapping")

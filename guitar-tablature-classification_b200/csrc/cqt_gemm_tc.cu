@@ -186,7 +186,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   const int nkb = prm.parts * prm.kb_per_part;
   const int n_splits = (nkb + prm.kb_per_split - 1) / prm.kb_per_split;
   const int64_t n_tiles = prm.m_tiles * prm.n_chunks;
+#ifdef TC_EXP_SKIP_OLO   // timing experiment only (wrong results): is the kernel bound by operand delivery from L2?
+  constexpr uint32_t stage_tx = 2 * X_TILE_BYTES + 1 * (uint32_t)NC * TBK * 4;
+#else
   constexpr uint32_t stage_tx = 2 * X_TILE_BYTES + 2 * (uint32_t)NC * TBK * 4;
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -209,7 +213,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           tma_load_2d(st_xhi(stage), &tm_xhi, bar_full(stage), kx, row0 + p);
           tma_load_2d(st_xlo(stage), &tm_xlo, bar_full(stage), kx, row0 + p);
           tma_load_2d(st_ohi(stage), &tm_ohi, bar_full(stage), kb * EPK, n0);
+#ifndef TC_EXP_SKIP_OLO
           tma_load_2d(st_olo(stage), &tm_olo, bar_full(stage), kb * EPK, n0);
+#endif
           if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
         }
       }

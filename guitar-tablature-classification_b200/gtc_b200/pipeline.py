@@ -10,6 +10,7 @@ already resident in HBM and no copies are issued (the kernel-only number of benc
 """
 from __future__ import annotations
 
+import time
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional
 
@@ -96,6 +97,7 @@ class FrontEnd:
         self._bufs = {}
         self.patch_events = None       # set to a list to collect (start_event, end_event, n_segments) of every patch launch
         self.gemm_events = None        # same for every GEMM + dB-finish pair
+        self._meta_plan, self._meta_ev, self._meta_sizes = None, None, None
         self.trace = None              # set to a list to collect (label, stream name, event) marks: scripts/timeline.py
 
     # ------------------------------------------------------------------ host-side planning (integer arithmetic only)
@@ -154,7 +156,7 @@ class FrontEnd:
         if self.trace is not None:
             e = torch.cuda.Event(enable_timing=True)
             e.record(stream)
-            self.trace.append((label, name, e))
+            self.trace.append((label, name, e, time.perf_counter()))
 
     def _buf(self, name, shape, dtype, pinned=False):
         key = (name, pinned)
@@ -193,16 +195,22 @@ class FrontEnd:
         ev_ws = [None, None]                                                          # GEMM that last read ws2[b]
         pb = min(self.patch_batch, max(1, max_seg))
         ev_free = [[], []]
-        # all chunk metadata (offsets, label times) goes up in one copy from pinned memory
-        meta_np = np.concatenate([np.concatenate([c.clip_off, c.seg_off, c.evt_off]) for c in chunks]).astype(np.int64) \
-            if chunks else np.zeros(1, np.int64)
-        time_np = np.concatenate([c.seg_time for c in chunks]) if chunks else np.zeros(1)
-        h_meta = self._buf("meta_host", (meta_np.size,), torch.int64, pinned=True)
-        h_time = self._buf("time_host", (max(1, time_np.size),), torch.float64, pinned=True)
-        h_meta.numpy()[:] = meta_np
-        h_time.numpy()[: time_np.size] = time_np
-        d_meta_all = self._buf("meta_dev", (meta_np.size,), torch.int64)
-        d_time_all = self._buf("time_dev", (max(1, time_np.size),), torch.float64)
+        # all chunk metadata (offsets, label times) goes up in one copy from pinned memory; with device-resident inputs a
+        # chunk plan that is passed in again (same list object: epochs over the same shard) keeps its device copy
+        reuse_meta = device_inputs and self._meta_plan is not None and self._meta_plan is chunks
+        if not reuse_meta:
+            meta_np = np.concatenate([np.concatenate([c.clip_off, c.seg_off, c.evt_off]) for c in chunks]).astype(np.int64) \
+                if chunks else np.zeros(1, np.int64)
+            time_np = np.concatenate([c.seg_time for c in chunks]) if chunks else np.zeros(1)
+            if self._meta_ev is not None:
+                self._meta_ev.synchronize()      # the previous run's async upload has read the pinned staging buffers
+            h_meta = self._buf("meta_host", (meta_np.size,), torch.int64, pinned=True)
+            h_time = self._buf("time_host", (max(1, time_np.size),), torch.float64, pinned=True)
+            h_meta.numpy()[:] = meta_np
+            h_time.numpy()[: time_np.size] = time_np
+            self._meta_sizes = (meta_np.size, max(1, time_np.size), meta_np.nbytes + time_np.nbytes)
+        d_meta_all = self._buf("meta_dev", (self._meta_sizes[0],), torch.int64)
+        d_time_all = self._buf("time_dev", (self._meta_sizes[1],), torch.float64)
         with torch.cuda.device(self.device):
             stats.zero_()
             self.s_copy.wait_stream(torch.cuda.current_stream())
@@ -210,11 +218,15 @@ class FrontEnd:
             self.s_comp.wait_stream(torch.cuda.current_stream())
             self.s_out.wait_stream(torch.cuda.current_stream())
             self.s_patch.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self.s_copy):
-                d_meta_all.copy_(h_meta, non_blocking=True)
-                d_time_all.copy_(h_time, non_blocking=True)
-                if not device_inputs:
-                    out.h2d_bytes += meta_np.nbytes + time_np.nbytes
+            if not reuse_meta:
+                with torch.cuda.stream(self.s_copy):
+                    d_meta_all.copy_(h_meta, non_blocking=True)
+                    d_time_all.copy_(h_time, non_blocking=True)
+                    self._meta_ev = torch.cuda.Event()
+                    self._meta_ev.record(self.s_copy)
+                self._meta_plan = chunks
+            if not device_inputs:
+                out.h2d_bytes += self._meta_sizes[2]      # host-input runs upload their metadata every time
             def emit(job, gate, s_p):
                 jb, jch, j_db, j_tabs, _ = job
                 jng = jch.g1 - jch.g0

@@ -12,7 +12,7 @@ try:
     d = json.loads(lines[-1])
     print(label, "value", round(d["value"]), "ms", round(d["ms_per_step"], 2), "e2e", round(d["e2e"]["value"]), "e2e_ms",
           round(d["e2e"]["ms_per_step"], 2), "patch_frac", round(d["roofline"]["frac"], 3), "gemm_ms", round(d.get("gemm_live",{}).get("launch_ms",0),3), "patch_ms", round(d["roofline"]["launch_ms"],3), "path_frac",
-          round(d["path_roofline"]["frac_of_hbm_peak"], 3), "clk", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+          round(d["path_roofline"]["frac_of_hbm_peak"], 3), "host_ms", round(d.get("host_enqueue_ms_per_step", 0), 2), "clk", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
     print("   per-launch patch ms:", d["roofline"].get("per_launch_ms"))
 except Exception as e:
     print(label, "FAILED", e)

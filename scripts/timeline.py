@@ -26,18 +26,21 @@ for _ in range(3):
     fe.run(inp, device_inputs=not a.host)
 torch.cuda.synchronize()
 fe.trace = []
+import time
 base = torch.cuda.Event(enable_timing=True); base.record()
-for _ in range(a.steps):
+h0 = time.perf_counter()
+for i in range(a.steps):
     fe.run(inp, device_inputs=not a.host)
+    print(f"host: run() {i} returned at {1e3 * (time.perf_counter() - h0):.3f} ms")
 end = torch.cuda.Event(enable_timing=True); end.record()
 torch.cuda.synchronize()
-rows = sorted(((base.elapsed_time(e), lab, st) for lab, st, e in fe.trace))
+rows = sorted(((base.elapsed_time(e), lab, st, 1e3 * (h - h0)) for lab, st, e, h in fe.trace))
 print("total ms", base.elapsed_time(end))
 open_at = {}
-for t, lab, st in rows:
+for t, lab, st, h in rows:      # device time of the mark, host time at which it was enqueued
     if lab.endswith("<"):
         open_at[lab[:-1]] = t
-        print(f"{t:9.3f}  {st:6s} {lab}")
+        print(f"{t:9.3f}  (host {h:8.3f})  {st:6s} {lab}")
     else:
         k = lab[:-1]; t0 = open_at.get(k)
-        print(f"{t:9.3f}  {st:6s} {lab}" + (f"   dur {t - t0:.3f}" if t0 is not None else ""))
+        print(f"{t:9.3f}  (host {h:8.3f})  {st:6s} {lab}" + (f"   dur {t - t0:.3f}" if t0 is not None else ""))
