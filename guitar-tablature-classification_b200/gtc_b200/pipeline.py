@@ -98,13 +98,15 @@ class FrontEnd:
         self.patch_events = None       # set to a list to collect (start_event, end_event, n_segments) of every patch launch
         self.gemm_events = None        # same for every GEMM + dB-finish pair
         self._meta_plan, self._meta_ev, self._meta_sizes = None, None, None
+        self.stage_bytes_limit = 4 << 30   # host-input shards up to this size are staged whole in HBM (else per-chunk double buffers)
+        self.stage_piece_clips = 8         # clips per host->device copy of the staging train
         self.trace = None              # set to a list to collect (label, stream name, event) marks: scripts/timeline.py
 
     # ------------------------------------------------------------------ host-side planning (integer arithmetic only)
     def plan_chunks(self, inp: ShardInputs, ramp: bool = False) -> List[_Chunk]:
         """Cut the shard into chunks of whole clips, at most ``chunk_segments`` segments each.  ``ramp=True`` (the host-input
-        path) makes the first chunks small (1/8, 1/4, 1/2 of the limit) and the last ones small again, so the un-overlapped
-        head (first host->device copy) and tail (last device->host copy) of the three-stream pipeline shrink 8-fold."""
+        path) makes the first chunks small (1/8 of the limit, growing x1.5), so the un-overlapped head of the pipeline
+        (first host->device copy) is short and the compute stream never waits for audio that is still on the bus."""
         r = self.recipe
         lens = np.asarray(inp.clip_lens, dtype=np.int64)
         nseg = ops.segment_counts(lens, self.plan.seg_len, self.plan.seg_hop)
@@ -115,16 +117,16 @@ class FrontEnd:
         full = self.chunk_segments
         sizes = []
         if ramp and total > 3 * full:
-            head, tail = [full // 8, full // 4, full // 2], [full // 2, full // 8]
-            body = total - sum(head) - sum(tail)
-            n_body = -(-body // full)
-            sizes = head + [-(-body // n_body)] * n_body + tail
+            # geometric x1.5 head: while chunk k is computed, the copy engine delivers about 1.1-1.5 x as many clips
+            # (PCIe ~46 GB/s of int16 PCM against ~31 clips/ms of compute), so every chunk finds its audio resident;
+            # no ramp-down: the last chunk's device->host copy (0.75 ms) hides under its own patch stores (1.5 ms)
+            sizes = [int(full * f) for f in (0.125, 0.19, 0.28, 0.42, 0.63, 0.95)] + [full]   # then greedy full chunks
         marks = np.cumsum(sizes) if sizes else None              # target cumulative segment counts of the chunk ends
         chunks, c0, k = [], 0, 0
         while c0 < n_clips:
             c1 = c0 + 1
             if marks is not None and k < len(marks) - 1:
-                while c1 < n_clips and seg_off[c1 + 1] <= marks[k] and seg_off[c1 + 1] - seg_off[c0] <= full:
+                while c1 < n_clips and seg_off[c1 + 1] - seg_off[c0] <= sizes[k]:
                     c1 += 1
             else:
                 while c1 < n_clips and seg_off[c1 + 1] - seg_off[c0] <= full:
@@ -251,6 +253,44 @@ class FrontEnd:
                     ev_p.record(s_p)
                 ev_free[jb].append(ev_p)
 
+            # ---- host inputs: the whole shard is staged in HBM by ONE train of copies in pieces of a few clips, issued
+            #      up front and independent of the compute chunks (a 360-clip shard is 0.48 GB of int16 PCM).  The copy
+            #      engine then never waits for a staging buffer to be released by a framing kernel, which with two
+            #      per-chunk buffers it did whenever compute lagged (profiles/r01k_timeline_host.log).
+            n_samples_all = chunks[-1].s1 if chunks else 0
+            n_evt_all = chunks[-1].e1 if chunks else 0
+            staged = (not device_inputs) and bool(chunks) and \
+                n_samples_all * inp.audio.element_size() <= self.stage_bytes_limit
+            piece_ev, piece_end = [], []
+            if staged:
+                clip_off_all = np.concatenate([[0], np.cumsum(np.asarray(inp.clip_lens, dtype=np.int64))])
+                d_audio_all = self._buf("audio_all", (n_samples_all,), inp.audio.dtype)
+                d_ev_all = self._buf("ev_all", (3, max(1, n_evt_all)), torch.float64)
+                n_clips_all = chunks[-1].c1
+                out.h2d_bytes += n_samples_all * inp.audio.element_size() + n_evt_all * 24
+
+                def stage_until(c_goal):
+                    """Enqueue staging copies until clip ``c_goal`` is covered (pieces are enqueued a few chunks ahead of
+                    the kernels that read them, so the first chunk's kernels are not queued behind 45 copy calls)."""
+                    c = piece_end[-1] if piece_end else 0
+                    with torch.cuda.stream(self.s_copy):
+                        while c < min(c_goal, n_clips_all):
+                            c_next = min(n_clips_all, c + self.stage_piece_clips)
+                            a0, a1 = int(clip_off_all[c]), int(clip_off_all[c_next])
+                            if c == 0:
+                                self._mark("h2d<", self.s_copy, "copy")
+                            d_audio_all[a0:a1].copy_(inp.audio[a0:a1], non_blocking=True)
+                            if c == 0:                                # all note events ride behind the first piece
+                                for j in range(3):
+                                    d_ev_all[j, :n_evt_all].copy_(inp.events[j, :n_evt_all], non_blocking=True)
+                            e = torch.cuda.Event()
+                            e.record(self.s_copy)
+                            piece_ev.append(e)
+                            piece_end.append(c_next)
+                            c = c_next
+                            if c == n_clips_all:
+                                self._mark("h2d>", self.s_copy, "copy")
+
             pending = None
             m_at = 0
             for k, ch in enumerate(chunks):
@@ -260,7 +300,13 @@ class FrontEnd:
                 m_at += 3 * (nc + 1)
                 d_time = d_time_all[ch.g0:ch.g1]
                 # ---- stage inputs
-                with torch.cuda.stream(self.s_copy):
+                if staged:
+                    stage_until(chunks[min(k + 3, len(chunks) - 1)].c1)
+                    d_audio = d_audio_all[ch.s0:ch.s1]
+                    d_on, d_du, d_pi = d_ev_all[0, ch.e0:ch.e1], d_ev_all[1, ch.e0:ch.e1], d_ev_all[2, ch.e0:ch.e1]
+                    ev_h2d = piece_ev[int(np.searchsorted(np.asarray(piece_end), ch.c1))]     # first piece that ends at or after clip c1
+                else:
+                  with torch.cuda.stream(self.s_copy):
                     if ev_pre[b] is not None:
                         self.s_copy.wait_event(ev_pre[b])             # chunk k-2's framing / label kernels have read audio{b}, ev{b}
                     self._mark(f"h2d{k}<", self.s_copy, "copy")
@@ -297,6 +343,8 @@ class FrontEnd:
                         self._mark(f"frame{k}<", self.s_pre, "pre")
                         plan.frame(d_audio, d_clip_off, d_seg_off, ng, ws2[b])
                         self._mark(f"frame{k}>", self.s_pre, "pre")
+                        ev_fr = torch.cuda.Event()
+                        ev_fr.record(self.s_pre)
                         ops.rasterize_tabs(d_on, d_du, d_pi, d_evt_off, d_time, d_seg_off, out=d_tabs, stats=stats)
                         self._mark(f"labels{k}>", self.s_pre, "pre")
                         out.launches += 2
@@ -305,7 +353,7 @@ class FrontEnd:
                 ev_pre[b] = ev_in
                 # ---- tensor-core contraction + dB finish
                 with torch.cuda.stream(self.s_comp):
-                    self.s_comp.wait_event(ev_in)
+                    self.s_comp.wait_event(ev_fr if ng else ev_in)    # the GEMM needs the framed rows, not the labels
                     for e in ev_free[b]:
                         self.s_comp.wait_event(e)                     # chunk k-2's patches / D2H released db{b}
                     ev_g = ev_in if self.overlap else None
@@ -320,6 +368,7 @@ class FrontEnd:
                             t1.record(self.s_comp)
                             self.gemm_events.append((t0, t1, ng))
                         out.launches += 2
+                    self.s_comp.wait_event(ev_in)                     # labels of this chunk: patch consumers and D2H read them
                     ev_k = torch.cuda.Event()
                     ev_k.record(self.s_comp)
                 ev_ws[b] = ev_k
