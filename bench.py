@@ -44,7 +44,7 @@ def workload_config(n_clips=N_CLIPS):
                         "cqt.py CQT+|.|^4+dB+cut, jam_to_tablature labels, ViT_dataloader (3,224,224) patches" % (n_clips, CLIP_SECONDS),
             "clips_per_gpu": n_clips, "segments_per_gpu": n_clips * segs, "sr": SR, "seg_len": 4410, "seg_hop": 2205,
             "n_bins": 96, "frames": 5, "patch": [3, 224, 224],
-            "cache": "per-step inputs (0.95 GB audio) and outputs (65 GB of patches through a 10 GB ring) exceed the 126 MB L2; no flush needed"}
+            "cache": "per-step inputs (0.95 GB audio) and outputs (65 GB of patches through an 11 GB ring) exceed the 126 MB L2; no flush needed"}
 
 
 # ======================================================================================================================
@@ -248,9 +248,10 @@ def run_cuda_arm(args):
     audio_host.copy_(audio_dev if args.host_audio == "f32" else pcm_dev)
     del pcm_dev
     lens = np.full(n_clips, n, dtype=np.int64)
+    from gtc_b200 import ops as _ops
     for kv in args.opt:
         k, v = kv.split("=")
-        __import__("gtc_b200.ops", fromlist=["set_option"]).set_option(int(k), int(v))
+        _ops.set_option(int(k), int(v))
     fe = FrontEnd(recipe, device=local_rank, engine=args.engine, chunk_segments=args.chunk_segments, patch_batch=args.patch_batch,
                   overlap=args.overlap, gemm_ctas=args.gemm_ctas, patch_ctas_per_sm=args.patch_ctas_per_sm,
                   coresident=args.coresident, wave_aware=not args.no_wave_aware)
@@ -315,9 +316,8 @@ def run_cuda_arm(args):
     db_all = fe._bufs[("db_all", False)][: n_seg * 480].view(n_seg, 96, 5)
     pb = min(pb, fe._bufs[("patch0", False)].numel() // (3 * 224 * 224))
     ring = fe._bufs[("patch0", False)][: pb * 3 * 224 * 224].view(pb, 3, 224, 224)
-    ops_set = __import__("gtc_b200.ops", fromlist=["set_option"])
-    ops_set.set_option(16, 0)                                   # time the patch kernel alone on the whole GPU
-    from gtc_b200 import ops
+    from gtc_b200 import ops, _lib
+    ops.set_option(_lib.GTC_OPT_PATCH_MAX_CTAS, 0)              # time the patch kernel alone on the whole GPU
     evs = []
     torch.cuda.synchronize()
     with torch.cuda.stream(fe.s_comp):
@@ -345,8 +345,6 @@ def run_cuda_arm(args):
     live_seg = float(np.mean([n for _, n in live])) if live else pb
     achieved = live_seg * PATCH_BYTES_PER_SEGMENT / (live_ms * 1e-3) / 1e9          # inside the timed steps
     isolated = pb * PATCH_BYTES_PER_SEGMENT / (patch_ms * 1e-3) / 1e9                # the kernel alone on the GPU
-    live = getattr(timed, "patch_launches", [])
-    live_seg = float(np.mean([n for _, n in live])) if live else pb
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "patch_kernel_traffic.json")))
@@ -367,7 +365,7 @@ def run_cuda_arm(args):
                              "unit": "GB/s", "frac": achieved / peak_hbm, "traffic": traffic,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                              "launch_ms": live_ms, "segments_per_launch": live_seg, "launches_timed": len(live),
-                             "how": "mean of per-launch CUDA events on the launching stream inside the timed steps (next chunk's framing/label kernels run beside it)",
+                             "how": "mean of per-launch CUDA events on the launching stream over every patch launch inside the timed steps",
                              "per_launch_ms": [round(t, 3) for t, _ in live], "per_launch_segments": [n for _, n in live],
                              "isolated": {"achieved": isolated, "frac": isolated / peak_hbm, "launch_ms": patch_ms, "segments_per_launch": pb}},
                 "gemm_live": {"kernel": "gemm_tc_kernel + finish_db_kernel", "launch_ms": float(np.mean([t for t, _ in getattr(timed, "gemm_launches", [(0.0, 0)])])),

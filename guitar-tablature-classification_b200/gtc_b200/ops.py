@@ -72,12 +72,8 @@ class CqtPlan:
         """Fraction of the persistent tcgen05 GEMM's last wave that is filled for a chunk of ``n_seg`` segments in
         ``n_clips`` clips: tiles = ceil(rows / 128) x ceil(n_out / tile width) are dealt round-robin to one CTA per SM
         (cqt_gemm_tc.cu), so a chunk of 3.4 waves costs as much as one of 4.0.  Used by the chunk planner."""
-        rows = int(n_seg) + int(n_clips) * (self.parts - 1)
-        n_out = 2 * self.n_bins * self.n_frames
-        nc = next((w for w in (256, 240, 192, 128, 64) if n_out % w == 0), 256)
-        tiles = -(-rows // 128) * -(-n_out // nc)
-        waves = -(-tiles // self.sm_count)
-        return tiles / float(waves * self.sm_count) if tiles else 1.0
+        from .chunks import wave_efficiency
+        return wave_efficiency(n_seg, n_clips, self.parts, 2 * self.n_bins * self.n_frames, self.sm_count)
 
     def configure(self, option: int, value: int) -> None:
         """Tuning knobs (GTC_OPT_TC_KSPLIT, GTC_OPT_GEMM_MAX_CTAS)."""

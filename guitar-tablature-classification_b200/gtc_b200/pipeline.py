@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
+from .chunks import plan_bounds
 from .cqt_design import CqtRecipe
 
 
@@ -112,31 +113,10 @@ class FrontEnd:
         nseg = ops.segment_counts(lens, self.plan.seg_len, self.plan.seg_hop)
         clip_off = np.concatenate([[0], np.cumsum(lens)])
         seg_off = np.concatenate([[0], np.cumsum(nseg)])
-        n_clips = len(lens)
-        total = int(seg_off[-1])
         full = self.chunk_segments
-        sizes = []
-        if ramp and total > 3 * full:
-            # geometric x1.5 head: while chunk k is computed, the copy engine delivers about 1.1-1.5 x as many clips
-            # (PCIe ~46 GB/s of int16 PCM against ~31 clips/ms of compute), so every chunk finds its audio resident;
-            # no ramp-down: the last chunk's device->host copy (0.75 ms) hides under its own patch stores (1.5 ms)
-            sizes = [int(full * f) for f in (0.125, 0.19, 0.28, 0.42, 0.63, 0.95)] + [full]   # then greedy full chunks
-        marks = np.cumsum(sizes) if sizes else None              # target cumulative segment counts of the chunk ends
-        chunks, c0, k = [], 0, 0
-        while c0 < n_clips:
-            c1 = c0 + 1
-            if marks is not None and k < len(marks) - 1:
-                while c1 < n_clips and seg_off[c1 + 1] - seg_off[c0] <= sizes[k]:
-                    c1 += 1
-            else:
-                while c1 < n_clips and seg_off[c1 + 1] - seg_off[c0] <= full:
-                    c1 += 1
-            if self.wave_aware and c1 < n_clips and c1 - c0 > 4:
-                # the largest chunk is not the cheapest: end it where the GEMM's last wave of tiles is full
-                lo = c0 + max(1, int(0.8 * (c1 - c0)))
-                c1 = max(range(lo, c1 + 1),
-                         key=lambda c: (round(self.plan.gemm_wave_efficiency(int(seg_off[c] - seg_off[c0]), c - c0), 2), c))
-            k += 1
+        eff = (lambda n, c: self.plan.gemm_wave_efficiency(n, c)) if self.wave_aware else None
+        chunks = []
+        for c0, c1 in plan_bounds(nseg, full, ramp=ramp, efficiency=eff):
             ch = _Chunk(c0, c1, int(clip_off[c0]), int(clip_off[c1]), int(seg_off[c0]), int(seg_off[c1]),
                         int(inp.evt_off[c0]), int(inp.evt_off[c1]))
             assert ch.g1 - ch.g0 <= max(self.chunk_segments, int(nseg[c0]))
@@ -151,7 +131,6 @@ class FrontEnd:
                     times.append((np.arange(n, dtype=np.float64) + 0.5) * (duration / n))
             ch.seg_time = np.concatenate(times) if times else np.zeros(0, dtype=np.float64)
             chunks.append(ch)
-            c0 = c1
         return chunks
 
     def _mark(self, label, stream, name):

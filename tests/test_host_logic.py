@@ -180,3 +180,37 @@ def test_inference_segment_tables():
     assert s.tolist() == [0] and v.tolist() == [5000]
     s, v, L = inference.vit_window_table(4000, 44100)                  # shorter than half a window: skipped (:317-318)
     assert len(s) == 0
+
+
+def test_chunk_planner_properties():
+    """gtc_b200/chunks.py: chunks tile the clip list exactly, respect the segment limit, end on full GEMM waves where a
+    choice exists, and ramp up from small chunks for the host-input path."""
+    from gtc_b200 import chunks as ck
+    sm, parts, n_out = 148, 2, 960
+    eff = lambda n, c: ck.wave_efficiency(n, c, parts, n_out, sm)
+    # BASELINE.json configs[1]: 360 clips of 299 segments
+    nseg = np.full(360, 299)
+    plain = ck.plan_bounds(nseg, 19200)
+    assert plain[0] == (0, 64) and plain[-1][1] == 360 and all(a1 == b0 for (_, a1), (b0, _) in zip(plain, plain[1:]))
+    wave = ck.plan_bounds(nseg, 19200, efficiency=eff)
+    assert [c1 - c0 for c0, c1 in wave] == [63, 63, 63, 63, 63, 45]                       # 63 clips = 18 900 rows = 592 tiles
+    assert ck.gemm_tiles(63 * 299, 63, parts, n_out) == 4 * sm and eff(63 * 299, 63) == 1.0
+    assert abs(eff(54 * 299, 54) - 508 / 592) < 1e-12                                     # the old 54-clip chunks: 3.43 waves
+    ramp = ck.plan_bounds(nseg, 19200, ramp=True, efficiency=eff)
+    sizes = [c1 - c0 for c0, c1 in ramp]
+    assert sizes[0] == 8 and sizes[:6] == sorted(sizes[:6]) and sum(sizes) == 360 and max(sizes) <= 64
+    assert all(b <= 1.7 * a + 1 for a, b in zip(sizes[:6], sizes[1:7]))                   # growth stays near x1.5
+    # ragged shard: zero-segment clips, one clip longer than the limit, random lengths
+    rng = np.random.default_rng(5)
+    nseg = rng.integers(0, 400, size=97)
+    nseg[10] = 0
+    nseg[40] = 5000
+    for ramp_on in (False, True):
+        for e in (None, eff):
+            b = ck.plan_bounds(nseg, 2000, ramp=ramp_on, efficiency=e)
+            assert b[0][0] == 0 and b[-1][1] == 97 and all(a1 == b0 for (_, a1), (b0, _) in zip(b, b[1:]))
+            for c0, c1 in b:
+                assert c1 > c0 and (nseg[c0:c1].sum() <= 2000 or c1 - c0 == 1)
+    assert ck.plan_bounds([], 100) == [] and ck.plan_bounds([7], 100) == [(0, 1)]
+    # tile widths follow cqt_gemm_tc.cu: 960 -> 240, 840*... ragged -> 256
+    assert ck.gemm_tiles(128, 0, 1, 960) == 4 and ck.gemm_tiles(129, 0, 1, 960) == 8 and ck.gemm_tiles(128, 0, 1, 2 * 84 * 130) == -(-21840 // 240)
