@@ -139,3 +139,55 @@ def test_host_staging_modes_agree(lib, shard_inputs, recipe):
     so = np.concatenate([[0], np.cumsum(counts)])
     want = np.concatenate([res["staged"][0][so[c]:so[c + 1]] for c in np.arange(len(lens))[::-1]])
     assert np.array_equal(res["staged_rev"][0], want)
+
+
+def test_full_size_shard_spot_checks(lib, recipe, basis_cache):
+    """BASELINE.json configs[1] at full size (360 clips x 30 s, 107 640 segments, the chunks bench.py times): the
+    pipeline's dB features, labels and patches of 48 randomly chosen segments against the CPU oracle, plus whole-run
+    invariants (value set, 0 dB peak per segment, identical channels, label stats)."""
+    from gtc_b200 import synth
+    from gtc_b200.pipeline import FrontEnd, ShardInputs
+    from oracle import cqt_oracle as co
+    dev = torch.device("cuda")
+    n_clips, n = 360, SR * 30
+    audio = synth.pluck_clips(n_clips, n, sr=SR, seed=1, device=dev, block=24).reshape(-1)
+    on, du, pi, eoff = synth.note_events([30.0] * n_clips, seed=2)
+    ev = np.stack([on, du, pi])
+    lens = np.full(n_clips, n, dtype=np.int64)
+    fe = FrontEnd(recipe)
+    n_seg = n_clips * 299
+    rng = np.random.default_rng(11)
+    picks = np.sort(rng.choice(n_seg, size=48, replace=False))
+    grabbed = {}
+    chan_diff = []
+
+    def consumer(patches, tabs, g0):
+        sel = picks[(picks >= g0) & (picks < g0 + patches.shape[0])]
+        for g in sel:
+            grabbed[int(g)] = patches[int(g) - g0].clone()
+        chan_diff.append(((patches[:, 0] != patches[:, 1]) | (patches[:, 0] != patches[:, 2])).any())
+
+    inp = ShardInputs(audio, lens, torch.from_numpy(ev).to(dev), eoff, sr=SR)
+    out = fe.run(inp, device_inputs=True, consumer=consumer)
+    torch.cuda.synchronize()
+    assert out.n_seg == n_seg and len(fe.plan_chunks(inp)) == 6 and len(grabbed) == 48
+    assert not any(bool(c) for c in chan_diff)                      # ViT_dataloader.py:50 repeat(3, 1, 1)
+    db = out.db
+    assert bool(((db == -120) | ((db >= -60) & (db <= 0))).all())  # cqt_lim value set
+    assert bool((db.amax(dim=(1, 2)) == 0).all())                   # ref=np.amax: every segment peaks at exactly 0 dB
+    tabs = out.tabs.cpu().numpy()
+    stats = fe.stats()
+    assert list(stats) == [n_seg, int((tabs.sum(axis=(1, 2)) > 0).sum()), int((tabs[:, 0].sum(axis=1) > 0).sum())]
+    db_h = db.cpu().numpy()
+    audio_h = audio.cpu().numpy()
+    tol = 0.01
+    for g in picks:
+        c, i = divmod(int(g), 299)
+        seg = audio_h[c * n + i * 2205: c * n + i * 2205 + 4410]
+        _, pre, _ = co.segment_features(seg, SR, fmin=co.note_to_hz_C(1), _basis_cache=basis_cache, return_pre_cut=True)
+        above, below = pre > -60 + 2 * tol, pre < -60 - 2 * tol
+        assert np.abs(db_h[g][above] - pre[above]).max() < tol and (db_h[g][below] == -120).all(), f"segment {g}"
+        t = lo.segment_times(30.0, 299)[i:i + 1]
+        want = lo.rasterize_events_numpy(ev[0, eoff[c]:eoff[c + 1]], ev[1, eoff[c]:eoff[c + 1]], ev[2, eoff[c]:eoff[c + 1]], t)[0]
+        assert np.array_equal(tabs[g], want), f"labels of segment {g}"
+        assert np.abs(grabbed[int(g)][0].cpu().numpy() - po.vit_patch(db_h[g])).max() < 3e-5, f"patch of segment {g}"
