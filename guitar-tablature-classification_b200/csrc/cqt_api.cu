@@ -38,7 +38,7 @@ static inline float tf32_rn_host(float x) {
 
 struct Workspace {
   int64_t n_rows, n_rows_pad, n_rows_alloc;
-  size_t off_xhi, off_xlo, off_out, off_rowmax, total;
+  size_t off_xhi, off_xlo, off_out, off_rowmax, off_done, total;
 };
 
 static Workspace workspace_layout(const PlanImpl& p, int64_t n_seg, int64_t n_clips, bool complex_out) {
@@ -54,6 +54,7 @@ static Workspace workspace_layout(const PlanImpl& p, int64_t n_seg, int64_t n_cl
   w.off_xlo = take(xbytes);
   w.off_out = take(obytes);
   w.off_rowmax = take((size_t)w.n_rows_pad * sizeof(float));
+  w.off_done = take((size_t)(w.n_rows_pad / 128) * sizeof(int));      // row-block counters of the fused dB finish
   w.total = o;
   return w;
 }
@@ -115,6 +116,8 @@ extern "C" int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int 
   p.engine = gemm_engine;
   p.sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("GTC_TC_KSPLIT")) p.tc_kb_per_split = atoi(e);
+  p.tc_fuse_finish = 0;                                 // measured slower than the separate pass, see cqt_gemm_tc.cu
+  if (const char* e = getenv("GTC_FUSE_FINISH")) p.tc_fuse_finish = atoi(e) != 0;
   if (tensor && (p.n_out % 16 != 0)) {
     delete plan;
     set_error("gtc_cqt_plan_create: tcgen05 engine needs 2*n_bins*n_frames %% 16 == 0 (got %d)", p.n_out);
@@ -191,6 +194,7 @@ extern "C" int gtc_cqt_plan_configure(gtc_plan* plan, int option, int value) {
   switch (option) {
     case GTC_OPT_TC_KSPLIT: plan->impl.tc_kb_per_split = value; return GTC_OK;
     case GTC_OPT_GEMM_MAX_CTAS: plan->impl.tc_max_ctas = value; return GTC_OK;
+    case GTC_OPT_FUSE_FINISH: plan->impl.tc_fuse_finish = value != 0; return GTC_OK;
     default: set_error("gtc_cqt_plan_configure: unknown option %d", option); return GTC_E_ARG;
   }
 }
@@ -227,16 +231,26 @@ static int run_segments(const gtc_plan* plan, const void* d_audio, const int64_t
   void* xlo = ws + w.off_xlo;
   float* gout = reinterpret_cast<float*>(ws + w.off_out);
   float* rowmax = reinterpret_cast<float*>(ws + w.off_rowmax);
+  int* tile_done = reinterpret_cast<int*>(ws + w.off_done);
   int rc = GTC_OK;
-  if (stages & 1) rc = launch_frame(p, d_audio, pcm16, d_clip_off, d_seg_off, (int)n_clips, w.n_rows, w.n_rows_alloc, xhi, xlo, rowmax, st);
+  if (stages & 1) rc = launch_frame(p, d_audio, pcm16, d_clip_off, d_seg_off, (int)n_clips, w.n_rows, w.n_rows_alloc, xhi, xlo, rowmax, tile_done, st);
   if (rc != GTC_OK || (stages & 2) == 0) return rc;
   float* mag2 = complex_out ? nullptr : gout;
   float* cplx = complex_out ? gout : nullptr;
+  FinishArgs fin;
+  memset(&fin, 0, sizeof(fin));
+  const bool fused = p.engine != GTC_GEMM_SIMT_FP32 && !complex_out && p.tc_fuse_finish;
+  if (fused) {
+    fin.out_db = d_out; fin.seg_off = d_seg_off; fin.tile_done = tile_done;
+    fin.n_clips = (int)n_clips; fin.parts = p.parts; fin.n_bins = p.n_bins; fin.n_frames = p.n_frames;
+    fin.n_rows = w.n_rows; fin.n_seg = n_seg;
+    fin.power = power; fin.amin = amin; fin.top_db = top_db; fin.cut_db = cut_db; fin.floor_db = floor_db;
+  }
   if (p.engine != GTC_GEMM_SIMT_FP32)
-    rc = launch_gemm_tc(p, xhi, xlo, w.n_rows_pad, w.n_rows_alloc, mag2, cplx, rowmax, st);
+    rc = launch_gemm_tc(p, xhi, xlo, w.n_rows_pad, w.n_rows_alloc, mag2, cplx, rowmax, fin, st);
   else
     rc = launch_gemm_simt(p, (const float*)xhi, (const float*)xlo, w.n_rows_pad, mag2, cplx, rowmax, st);
-  if (rc != GTC_OK) return rc;
+  if (rc != GTC_OK || fused) return rc;
   if (complex_out) return launch_finish_complex(p, cplx, d_seg_off, (int)n_clips, n_seg, d_out, st);
   return launch_finish_db(p, mag2, rowmax, d_seg_off, (int)n_clips, n_seg, d_out, power, amin, top_db, cut_db, floor_db, st);
 }

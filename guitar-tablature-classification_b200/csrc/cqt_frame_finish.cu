@@ -51,10 +51,13 @@ template <typename T, typename In>
 __global__ void __launch_bounds__(256)
 frame_kernel(const In* __restrict__ audio, const int64_t* __restrict__ clip_off, const int64_t* __restrict__ seg_off,
              int n_clips, int parts, int row_len, int seg_hop, int kp, int64_t n_rows, int64_t n_rows_alloc,
-             T* __restrict__ xhi, T* __restrict__ xlo, float scale, float* __restrict__ rowmax, int64_t n_rowmax) {
+             T* __restrict__ xhi, T* __restrict__ xlo, float scale, float* __restrict__ rowmax, int64_t n_rowmax,
+             int* __restrict__ tile_done) {
   const int vec_per_row = kp >> 2;
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  if (blockIdx.x == 0)                                   // row-block completion counters of the fused GEMM epilogue
+    for (int64_t i = threadIdx.x; i < (n_rowmax >> 7); i += blockDim.x) tile_done[i] = 0;
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows_alloc; row += warps_total) {
     int64_t base = 0, clip_end = 0;                 // clip_end == 0: a padding row, all zeros
     if (row < n_rows) {
@@ -88,7 +91,7 @@ frame_kernel(const In* __restrict__ audio, const int64_t* __restrict__ clip_off,
 template <typename In>
 static int launch_frame_t(const PlanImpl& p, const In* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
                           int n_clips, int64_t n_rows, int64_t n_rows_alloc, void* d_xhi, void* d_xlo, float* d_rowmax,
-                          cudaStream_t st) {
+                          int* d_tile_done, cudaStream_t st) {
   int64_t blocks = ceil_div(n_rows_alloc, 8);
   const int64_t cap = (int64_t)p.sm_count * 16;
   if (blocks > cap) blocks = cap;
@@ -96,21 +99,21 @@ static int launch_frame_t(const PlanImpl& p, const In* d_audio, const int64_t* d
   if (p.elem_bytes == 2)
     frame_kernel<__half, In><<<(unsigned)blocks, 256, 0, st>>>(d_audio, d_clip_off, d_seg_off, n_clips, p.parts, p.row_len,
                                                           p.seg_hop, p.kp, n_rows, n_rows_alloc, (__half*)d_xhi, (__half*)d_xlo,
-                                                          p.x_scale, d_rowmax, n_rowmax);
+                                                          p.x_scale, d_rowmax, n_rowmax, d_tile_done);
   else
     frame_kernel<float, In><<<(unsigned)blocks, 256, 0, st>>>(d_audio, d_clip_off, d_seg_off, n_clips, p.parts, p.row_len,
                                                          p.seg_hop, p.kp, n_rows, n_rows_alloc, (float*)d_xhi, (float*)d_xlo,
-                                                         1.f, d_rowmax, n_rowmax);
+                                                         1.f, d_rowmax, n_rowmax, d_tile_done);
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;
 }
 
 int launch_frame(const PlanImpl& p, const void* d_audio, int pcm16, const int64_t* d_clip_off, const int64_t* d_seg_off,
                  int n_clips, int64_t n_rows, int64_t n_rows_alloc, void* d_xhi, void* d_xlo, float* d_rowmax,
-                 cudaStream_t st) {
+                 int* d_tile_done, cudaStream_t st) {
   if (pcm16)
-    return launch_frame_t(p, (const int16_t*)d_audio, d_clip_off, d_seg_off, n_clips, n_rows, n_rows_alloc, d_xhi, d_xlo, d_rowmax, st);
-  return launch_frame_t(p, (const float*)d_audio, d_clip_off, d_seg_off, n_clips, n_rows, n_rows_alloc, d_xhi, d_xlo, d_rowmax, st);
+    return launch_frame_t(p, (const int16_t*)d_audio, d_clip_off, d_seg_off, n_clips, n_rows, n_rows_alloc, d_xhi, d_xlo, d_rowmax, d_tile_done, st);
+  return launch_frame_t(p, (const float*)d_audio, d_clip_off, d_seg_off, n_clips, n_rows, n_rows_alloc, d_xhi, d_xlo, d_rowmax, d_tile_done, st);
 }
 
 // one warp per segment
@@ -121,34 +124,10 @@ finish_db_kernel(const float* __restrict__ mag2, const float* __restrict__ rowma
   const int lane = threadIdx.x & 31;
   const int n_mag = n_bins * n_frames;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const float amin2 = amin * amin;
   for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < n_seg; g += warps_total) {
     const int c = find_clip(seg_off, n_clips, g);
     const int64_t row = g + (int64_t)c * (parts - 1);
-    const float* src = mag2 + row * n_mag;
-    // S = |C|^power ; amplitude_to_db squares it again: 10*log10(max(amin^2, S^2)) - 10*log10(max(amin^2, ref^2))
-    const float m2max = rowmax[row];
-    auto s_of = [&](float m2) -> float {
-      // |C|^power from |C|^2 : power 4 -> m2*m2 ; power 2 -> m2 ; power 1 -> sqrt(m2) ; else powf
-      if (power == 4.f) return m2 * m2;
-      if (power == 2.f) return m2;
-      if (power == 1.f) return sqrtf(m2);
-      return powf(m2, 0.5f * power);
-    };
-    const float ref = s_of(m2max);
-    const float ref_db = 10.f * log10f(fmaxf(amin2, ref * ref));
-    // log_spec.max() is the peak element's own value, max(amin^2, ref^2) -> exactly 0 dB
-    const float lo_clamp = 0.f - top_db;
-    float* dst = out + g * n_mag;
-    for (int o = lane; o < n_mag; o += 32) {
-      // out is [bin][t]; mag2 is [t][bin]
-      const int bin = o / n_frames, t = o - bin * n_frames;
-      const float s = s_of(src[t * n_bins + bin]);
-      float db = 10.f * log10f(fmaxf(amin2, s * s)) - ref_db;
-      db = fmaxf(db, lo_clamp);
-      if (db < cut_db) db = floor_db;
-      dst[o] = db;
-    }
+    finish_row_db(mag2 + row * n_mag, rowmax[row], out + g * n_mag, lane, n_bins, n_frames, power, amin, top_db, cut_db, floor_db);
   }
 }
 

@@ -44,6 +44,7 @@ struct TcParams {
   float* mag2;           // [rows][n_out/2] or null
   float* cplx;           // [rows][n_out]   or null
   float* rowmax;         // [rows]
+  FinishArgs fin;        // fin.out_db != null: the CTA that completes the last N tile of a 128-row block also does its dB finish
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -157,6 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bars[2 * TSTAGES + 4];
   __shared__ uint32_t s_tmem_slot;
+  __shared__ int s_block_done;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // stage s : [Xhi 16K][Xlo 16K][Ohi 32K][Olo 32K]
   auto st_xhi = [&](int s) { return smem_base + s * STAGE_BYTES; };
@@ -321,6 +323,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           }
         }
         atomicMax(reinterpret_cast<int*>(prm.rowmax + row), __float_as_int(rmax));
+        // ---- optional fused dB finish (cqt.py:56-58; GTC_OPT_FUSE_FINISH, off by default).  The reference level is the
+        //      segment's maximum over ALL its outputs, i.e. over the n_chunks N tiles of this 128-row block, which
+        //      different CTAs compute.  Every tile publishes its |C|^2 and row maxima (fence), then bumps the block's
+        //      counter; the CTA that brings it to n_chunks owns the finished block and converts it (8 warps x 16
+        //      segments, |C|^2 re-read from L2 where it was just written) while its MMA warp runs ahead into the next
+        //      tile (two TMEM stages = two K splits = 12 us of slack).
+        //      Measured on B200 (profiles/r01k_fused_finish.md): 0.58 ms per 18 900-row chunk against 0.35 ms for
+        //      GEMM + the separate finish_db_kernel.  The re-reads queue behind the TMA operand stream that keeps this
+        //      SM's L2 port busy, a block costs ~60 us instead of the 12 us of slack, and the stall repeats every wave;
+        //      the stand-alone pass spreads the same 36 MB over all SMs with nothing else in flight (28 us).
+        if (prm.fin.out_db != nullptr) {
+          const FinishArgs& f = prm.fin;
+          __threadfence();
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+          if (warp == 2 && lane == 0) s_block_done = atomicAdd(f.tile_done + m_tile, 1) == prm.n_chunks - 1;
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+          if (s_block_done) {
+            __threadfence();
+            const int n_mag = f.n_bins * f.n_frames;
+            // clip of the block's first row (rows of clip c start at seg_off[c] + c*(P-1)); later rows only step forward
+            int c = 0;
+            int64_t row_lo = 0, row_hi = 0, seg_hi = 0;              // clip c owns rows [row_lo, row_hi), segments < seg_hi
+            {
+              const int64_t r0 = m_tile * TBM + (warp - 2);
+              int lo = 0, hi = f.n_clips;
+              while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(f.seg_off + mid) + (int64_t)mid * (f.parts - 1) <= r0) lo = mid; else hi = mid;
+              }
+              c = lo;
+              row_lo = __ldg(f.seg_off + c) + (int64_t)c * (f.parts - 1);
+              seg_hi = __ldg(f.seg_off + c + 1);
+              row_hi = seg_hi + (int64_t)(c + 1) * (f.parts - 1);
+            }
+            for (int i = warp - 2; i < TBM; i += TC_EPI_WARPS) {
+              const int64_t r = m_tile * TBM + i;
+              if (r >= f.n_rows) break;
+              while (r >= row_hi && c + 1 < f.n_clips) {
+                ++c;
+                row_lo = row_hi;
+                seg_hi = __ldg(f.seg_off + c + 1);
+                row_hi = seg_hi + (int64_t)(c + 1) * (f.parts - 1);
+              }
+              const int64_t g = r - (int64_t)c * (f.parts - 1);      // the clip's last P-1 rows start no segment
+              if (g >= seg_hi) continue;
+              finish_row_db(prm.mag2 + r * n_mag, __ldcg(prm.rowmax + r), f.out_db + g * n_mag, lane, f.n_bins, f.n_frames,
+                            f.power, f.amin, f.top_db, f.cut_db, f.floor_db);
+            }
+            if (warp == 2 && lane == 0) f.tile_done[m_tile] = 0;     // ready for the next contraction over this workspace
+          }
+        }
       }
     }
   }
@@ -421,7 +474,7 @@ static void launch_nc(bool cplx, bool half, unsigned grid, cudaStream_t st, cons
 }
 
 int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int64_t n_rows_pad, int64_t n_rows_alloc,
-                   float* d_mag2, float* d_cplx, float* d_rowmax, cudaStream_t st) {
+                   float* d_mag2, float* d_cplx, float* d_rowmax, const FinishArgs& fin, cudaStream_t st) {
   GTC_REQUIRE(p.tmap_op_hi != nullptr, GTC_E_ARG, "plan was not created with the tcgen05 engine");
   CUtensorMap tm_xhi, tm_xlo;
   int rc = encode_2d(&tm_xhi, d_xhi, (uint64_t)n_rows_alloc, (uint64_t)p.kp, TBM, p.elem_bytes);
@@ -438,6 +491,8 @@ int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int6
   prm.parts = p.parts;
   prm.m_tiles = n_rows_pad / TBM;
   prm.mag2 = d_mag2; prm.cplx = d_cplx; prm.rowmax = d_rowmax;
+  prm.fin = fin;
+  if (d_cplx != nullptr) prm.fin.out_db = nullptr;
   const int64_t n_tiles = prm.m_tiles * prm.n_chunks;
   const int64_t max_ctas = p.tc_max_ctas > 0 && p.tc_max_ctas < p.sm_count ? p.tc_max_ctas : p.sm_count;
   const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);

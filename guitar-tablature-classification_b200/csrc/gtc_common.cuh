@@ -44,6 +44,66 @@ __device__ __forceinline__ int find_clip(const int64_t* __restrict__ off, int n,
   return lo;
 }
 
+// ---- dB finish of one segment (cqt.py:56-58), shared by finish_db_kernel and the fused tcgen05 epilogue so that both
+//      produce the same bits: |C|^2 -> |C|^power -> librosa.amplitude_to_db(ref=np.amax, amin, top_db) -> cqt_lim.
+struct FinishArgs {
+  float* out_db;             // [n_seg][n_bins][n_frames]; null = do not fuse (the caller runs finish_db_kernel)
+  const int64_t* seg_off;    // [n_clips + 1]
+  int* tile_done;            // [n_rows_pad / 128] counters, zero before the launch (frame_kernel) and after it
+  int n_clips, parts, n_bins, n_frames;
+  int64_t n_rows, n_seg;
+  float power, amin, top_db, cut_db, floor_db;
+};
+
+__device__ __forceinline__ float mag_power(float m2, float power) {
+  // |C|^power from |C|^2 : power 4 -> m2*m2 ; power 2 -> m2 ; power 1 -> sqrt(m2) ; else powf
+  if (power == 4.f) return m2 * m2;
+  if (power == 2.f) return m2;
+  if (power == 1.f) return sqrtf(m2);
+  return powf(m2, 0.5f * power);
+}
+
+// dB value of one element given the segment's reference (both as |C|^2)
+struct DbScale {
+  float power, amin2, ref_db, lo_clamp, cut_db, floor_db;
+  __device__ __forceinline__ DbScale(float m2max, float power_, float amin, float top_db, float cut_db_, float floor_db_)
+      : power(power_), amin2(amin * amin), cut_db(cut_db_), floor_db(floor_db_) {
+    // S = |C|^power ; amplitude_to_db squares it again: 10*log10(max(amin^2, S^2)) - 10*log10(max(amin^2, ref^2))
+    const float ref = mag_power(m2max, power);
+    ref_db = 10.f * log10f(fmaxf(amin2, ref * ref));
+    lo_clamp = 0.f - top_db;         // log_spec.max() is the peak element's own value -> exactly 0 dB
+  }
+  __device__ __forceinline__ float operator()(float m2) const {
+    const float s = mag_power(m2, power);
+    float db = 10.f * log10f(fmaxf(amin2, s * s)) - ref_db;
+    db = fmaxf(db, lo_clamp);
+    return db < cut_db ? floor_db : db;
+  }
+};
+
+// one warp: src = the segment's |C|^2 as [t][bin] (L2), dst = its dB features as [bin][t].  All of a row's loads are
+// issued before the first value is used (U x 32 elements per trip), so a row costs one L2 round trip, not n_mag / 32.
+template <int U = 16>
+__device__ __forceinline__ void finish_row_db(const float* src, float m2max, float* dst, int lane, int n_bins, int n_frames,
+                                              float power, float amin, float top_db, float cut_db, float floor_db) {
+  const int n_mag = n_bins * n_frames;
+  const DbScale scale(m2max, power, amin, top_db, cut_db, floor_db);
+  for (int o0 = lane; o0 < n_mag; o0 += 32 * U) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int o = o0 + 32 * u;
+      const int bin = o / n_frames, t = o - bin * n_frames;
+      v[u] = o < n_mag ? __ldcg(src + t * n_bins + bin) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int o = o0 + 32 * u;
+      if (o < n_mag) dst[o] = scale(v[u]);
+    }
+  }
+}
+
 // ---- segment-operator plan (cqt_api.cu) -------------------------------------------------------------------
 struct PlanImpl {
   int device;
@@ -60,6 +120,7 @@ struct PlanImpl {
   int sm_count;
   int tc_max_ctas;      // persistent GEMM grid limit (0 = sm_count)
   int tc_kb_per_split;  // K blocks per tensor-core accumulation split (0 = default), env GTC_TC_KSPLIT
+  int tc_fuse_finish;   // 1: the tcgen05 epilogue also does the dB finish (GTC_OPT_FUSE_FINISH; default 0, measured slower)
   float x_scale;    // fp16x2 engine: audio is multiplied by this power of two before the hi/lo split (1 otherwise)
   float out_scale;  // epilogue factor undoing x_scale and the operator's power-of-two scale (1 otherwise)
   float* d_op;      // [n_pad][k_total]  operator, fp32, K padded per part (SIMT engine only)
@@ -72,11 +133,11 @@ struct PlanImpl {
 // launchers (each enqueues on `st`, returns a GTC_* code); xhi/xlo element type follows PlanImpl::elem_bytes
 int launch_frame(const PlanImpl& p, const void* d_audio, int pcm16, const int64_t* d_clip_off, const int64_t* d_seg_off,
                  int n_clips, int64_t n_rows, int64_t n_rows_alloc, void* d_xhi, void* d_xlo, float* d_rowmax,
-                 cudaStream_t st);
+                 int* d_tile_done, cudaStream_t st);
 int launch_gemm_simt(const PlanImpl& p, const float* d_xhi, const float* d_xlo, int64_t n_rows_pad,
                      float* d_mag2, float* d_cplx, float* d_rowmax, cudaStream_t st);
 int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int64_t n_rows_pad, int64_t n_rows_alloc,
-                   float* d_mag2, float* d_cplx, float* d_rowmax, cudaStream_t st);
+                   float* d_mag2, float* d_cplx, float* d_rowmax, const FinishArgs& fin, cudaStream_t st);
 int tc_plan_init(PlanImpl& p);
 void tc_plan_free(PlanImpl& p);
 int launch_finish_db(const PlanImpl& p, const float* d_mag2, const float* d_rowmax, const int64_t* d_seg_off,

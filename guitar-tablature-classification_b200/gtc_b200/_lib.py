@@ -16,6 +16,7 @@ GTC_GEMM_SIMT_FP32 = 1
 GTC_GEMM_TCGEN05_FP16X2 = 2
 GTC_OPT_TC_KSPLIT = 1
 GTC_OPT_GEMM_MAX_CTAS = 2
+GTC_OPT_FUSE_FINISH = 3
 GTC_OPT_PATCH_MAX_CTAS = 16
 GTC_OPT_PATCH_CTAS_PER_SM = 17
 GTC_PATCH_VIT = 0
