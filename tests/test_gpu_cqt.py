@@ -155,3 +155,20 @@ def test_pcm16_input_is_bit_identical_to_librosa_fp32(plan, clips):
     got = plan.segments_db(torch.from_numpy(np.concatenate(pcm)).to(dev), torch.from_numpy(clip_off).to(dev),
                            torch.from_numpy(seg_off).to(dev), int(seg_off[-1])).cpu().numpy()
     assert np.array_equal(got, want)
+
+
+def test_fused_finish_option_is_bit_identical(recipe, lib, clips):
+    """GTC_OPT_FUSE_FINISH: the dB finish done by the tcgen05 epilogue (the CTA completing a 128-row block converts it)
+    gives the same bits as the separate finish_db_kernel, for ragged clips and for a chunk of several tile waves."""
+    from gtc_b200 import ops, _lib
+    big = [make_test_audio(SR * 3, seed=90 + i) for i in range(40)]            # 40 x 29 segments = 1160 rows = 10 row blocks
+    for engine in (ENGINES["fp16x2"], ENGINES["tcgen05"]):
+        p = ops.CqtPlan(recipe, engine=engine)
+        for cl in (clips, big):
+            p.configure(_lib.GTC_OPT_FUSE_FINISH, 0)
+            a = run_gpu(p, cl)
+            p.configure(_lib.GTC_OPT_FUSE_FINISH, 1)
+            b = run_gpu(p, cl)
+            c = run_gpu(p, cl)                                                    # counters are left clean for the next call
+            assert np.array_equal(a, b) and np.array_equal(b, c)
+        p.close()
