@@ -7,13 +7,17 @@ A chunk is a run of whole clips.  Its size decides two costs on the GPU (DESIGN.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
 GEMM_TILE_M = 128                           # cqt_gemm_tc.cu TBM
 GEMM_TILE_WIDTHS = (256, 240, 192, 128, 64)  # cqt_gemm_tc.cu kTileWidths: the first that divides n_out
-RAMP_FRACTIONS = (0.125, 0.19, 0.28, 0.42, 0.63, 0.95)   # host-input head: x1.5 per chunk, see plan_bounds()
+# host-input head, as fractions of the chunk limit: one, one, two, two, three, three quarters -- with the limit at four
+# GEMM waves these are chunks of 1, 1, 2, 2, 3, 3 FULL waves (the efficiency rule below trims 16/32/48 clips to 15/31/47),
+# so the small chunks of the ramp do not pay for half-empty waves.  GTC_RAMP="f0,f1,..." overrides it for experiments.
+RAMP_FRACTIONS = (0.25, 0.25, 0.5, 0.5, 0.75, 0.75)
 
 
 def gemm_tiles(n_seg: int, n_clips: int, parts: int, n_out: int) -> int:
@@ -43,7 +47,10 @@ def plan_bounds(n_seg_per_clip: Sequence[int], limit: int, ramp: bool = False,
     nseg = np.asarray(n_seg_per_clip, dtype=np.int64)
     seg_off = np.concatenate([[0], np.cumsum(nseg)])
     n_clips, total = len(nseg), int(seg_off[-1])
-    sizes = [int(limit * f) for f in RAMP_FRACTIONS] if ramp and total > 3 * limit else []
+    fractions = RAMP_FRACTIONS
+    if os.environ.get("GTC_RAMP"):
+        fractions = tuple(float(x) for x in os.environ["GTC_RAMP"].split(","))
+    sizes = [int(limit * f) for f in fractions] if ramp and total > 3 * limit else []
     bounds, c0, k = [], 0, 0
     while c0 < n_clips:
         cap = sizes[k] if k < len(sizes) else limit

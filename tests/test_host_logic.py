@@ -198,8 +198,8 @@ def test_chunk_planner_properties():
     assert abs(eff(54 * 299, 54) - 508 / 592) < 1e-12                                     # the old 54-clip chunks: 3.43 waves
     ramp = ck.plan_bounds(nseg, 19200, ramp=True, efficiency=eff)
     sizes = [c1 - c0 for c0, c1 in ramp]
-    assert sizes[0] == 8 and sizes[:6] == sorted(sizes[:6]) and sum(sizes) == 360 and max(sizes) <= 64
-    assert all(b <= 1.7 * a + 1 for a, b in zip(sizes[:6], sizes[1:7]))                   # growth stays near x1.5
+    assert sizes[:7] == [15, 15, 31, 31, 47, 47, 63] and sum(sizes) == 360 and max(sizes) <= 64   # 1,1,2,2,3,3,4 full waves
+    assert all(eff(299 * n, n) > 0.95 for n in sizes[:7])
     # ragged shard: zero-segment clips, one clip longer than the limit, random lengths
     rng = np.random.default_rng(5)
     nseg = rng.integers(0, 400, size=97)
