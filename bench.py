@@ -225,6 +225,19 @@ def run_cuda_arm(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: this framework has no CPU fallback")
+    numa = None
+    if args.numa_bind:
+        # run this rank's host thread (and first-touch its pinned staging buffers) on the CPUs NVML reports as local to
+        # the rank's GPU: the host-input arm moves 0.7 GB per step per GPU through the socket's PCIe root
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(physical_gpu_index(local_rank))
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+            numa = sorted(os.sched_getaffinity(0))
+            numa = f"{len(numa)} cpus {numa[0]}-{numa[-1]}"
+        except Exception as e:                      # no NVML / not permitted: run unbound
+            numa = f"unbound ({type(e).__name__})"
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
@@ -359,7 +372,8 @@ def run_cuda_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": out_e2e.h2d_bytes, "d2h_bytes_per_step": out_e2e.d2h_bytes,
                         "host_audio": "int16 PCM (the WAV files' samples; x/32768 on the device == librosa.load)" if args.host_audio == "pcm16" else "fp32",
-                        "note": "pinned host audio+events in, dB features + labels + stats back; patches stay in HBM for the engines"},
+                        "note": "pinned host audio+events in, dB features + labels + stats back; patches stay in HBM for the engines",
+                        "cpu_affinity": numa},
                 "gpu_launches": out_dev.launches * args.steps, "host_enqueue_ms_per_step": host_ms_dev,
                 "roofline": {"bound": "hbm", "kernel": "patch_kernel<5> (gtc_patches)", "achieved": achieved, "peak": peak_hbm,
                              "unit": "GB/s", "frac": achieved / peak_hbm, "traffic": traffic,
@@ -396,6 +410,7 @@ def main():
     ap.add_argument("--engine", type=int, default=None, help="GEMM engine: 0 tcgen05 3xTF32, 1 SIMT fp32, 2 tcgen05 fp16x2 (default: library default)")
     ap.add_argument("--coresident", action="store_true", help="experiment: patch kernels on their own stream under the next chunk GEMM (needs -DTC_MAXNREG=152; slower, see profiles/r01j_coresident.md)")
     ap.add_argument("--no-wave-aware", action="store_true", help="plain greedy chunks (largest that fit) instead of full GEMM tile waves")
+    ap.add_argument("--numa-bind", action="store_true", help="bind each rank to the CPUs local to its GPU before allocating pinned memory")
     ap.add_argument("--clock-period", type=float, default=0.02, help="seconds between NVML clock samples during the timed region (0 = off)")
     ap.add_argument("--opt", action="append", default=[], help="library option id=value (gtc_set_option), for experiments")
     ap.add_argument("--overlap", action="store_true", help="run each chunk's patch kernel beside the next chunk's GEMM (slower on B200, see profiles/)")
