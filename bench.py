@@ -279,8 +279,11 @@ def run_cuda_arm(args):
     # PAGEABLE host memory, which synchronises the stream first -- one hidden host sync per step.)
     stats_head = torch.tensor([n_clips, 0, int(lens.sum())], dtype=torch.int64).pin_memory()
 
-    def step(inp, device_inputs):
-        out = fe.run(inp, device_inputs=device_inputs, chunks=chunks if device_inputs else chunks_host)
+    def step(inp, device_inputs, last=False):
+        # host-input arm: the next step's shard (the same pinned buffers stand in for it) is prefetched behind this
+        # step's copies, as a training loop would do with the next shard of the corpus; the last step prefetches nothing
+        out = fe.run(inp, device_inputs=device_inputs, chunks=chunks if device_inputs else chunks_host,
+                     next_inp=inp if (args.prefetch and not device_inputs and not last) else None, next_chunks=chunks_host)
         # tiny per-shard stats gather (the path's only collective), jam_to_tablature.py:376-378
         stats_head[1] = out.n_seg
         stats_vec[:3].copy_(stats_head, non_blocking=True)
@@ -296,7 +299,7 @@ def run_cuda_arm(args):
 
     def timed(inp, device_inputs, steps, warmup):
         for _ in range(warmup):
-            step(inp, device_inputs)
+            step(inp, device_inputs, last=True)       # warm-up steps prefetch nothing: the timed region starts cold
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         fe.patch_events = [] if device_inputs else None      # per-launch CUDA events on the launching stream, timed region only
@@ -304,8 +307,8 @@ def run_cuda_arm(args):
         e0.record()
         out = None
         t_host = time.perf_counter()
-        for _ in range(steps):
-            out = step(inp, device_inputs)
+        for i in range(steps):
+            out = step(inp, device_inputs, last=(i == steps - 1))
         timed.host_ms = 1e3 * (time.perf_counter() - t_host) / max(1, steps)     # CPU time to enqueue one step
         e1.record()
         barrier()
@@ -382,6 +385,7 @@ def run_cuda_arm(args):
                         "h2d_bytes_per_step": out_e2e.h2d_bytes, "d2h_bytes_per_step": out_e2e.d2h_bytes,
                         "host_audio": "int16 PCM (the WAV files' samples; x/32768 on the device == librosa.load)" if args.host_audio == "pcm16" else "fp32",
                         "note": "pinned host audio+events in, dB features + labels + stats back; patches stay in HBM for the engines",
+                        "prefetch": bool(args.prefetch),
                         "cpu_affinity": numa},
                 "gpu_launches": out_dev.launches * args.steps, "host_enqueue_ms_per_step": host_ms_dev,
                 "roofline": {"bound": "hbm", "kernel": "patch_kernel<5> (gtc_patches)", "achieved": achieved, "peak": peak_hbm,
@@ -422,6 +426,7 @@ def main():
     ap.add_argument("--engine", type=int, default=None, help="GEMM engine: 0 tcgen05 3xTF32, 1 SIMT fp32, 2 tcgen05 fp16x2 (default: library default)")
     ap.add_argument("--coresident", action="store_true", help="experiment: patch kernels on their own stream under the next chunk GEMM (needs -DTC_MAXNREG=152; slower, see profiles/r01j_coresident.md)")
     ap.add_argument("--no-wave-aware", action="store_true", help="plain greedy chunks (largest that fit) instead of full GEMM tile waves")
+    ap.add_argument("--no-prefetch", dest="prefetch", action="store_false", help="e2e arm: do not start the next step's host->device copies under the current step")
     ap.add_argument("--numa-bind", action="store_true", help="bind each rank to the CPUs local to its GPU before allocating pinned memory")
     ap.add_argument("--clock-period", type=float, default=0.02, help="seconds between NVML clock samples during the timed region (0 = off)")
     ap.add_argument("--opt", action="append", default=[], help="library option id=value (gtc_set_option), for experiments")

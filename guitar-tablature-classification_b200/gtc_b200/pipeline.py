@@ -62,6 +62,65 @@ class _Chunk:
     seg_time: np.ndarray = field(default=None)
 
 
+class _Staging:
+    """One whole-shard staging slot of the host-input path: the shard's audio and note events are copied into HBM by a
+    train of piece copies on a stream of their own; consumers wait for the event of the piece they need."""
+
+    def __init__(self, fe: "FrontEnd", slot: int, inp: ShardInputs, chunks: List["_Chunk"], prev: Optional["_Staging"]):
+        n_clips = chunks[-1].c1
+        self.fe, self.slot, self.inp, self.n_clips, self.chunks = fe, slot, inp, int(n_clips), chunks
+        self.key = FrontEnd._stage_key(inp, chunks)
+        self.consumed = False
+        self.clip_off = np.concatenate([[0], np.cumsum(np.asarray(inp.clip_lens[:n_clips], dtype=np.int64))])
+        self.n_samples, self.n_evt = int(self.clip_off[-1]), int(inp.evt_off[n_clips])
+        self.audio = fe._buf(f"audio_all{slot}", (self.n_samples,), inp.audio.dtype)
+        self.events = fe._buf(f"ev_all{slot}", (3, max(1, self.n_evt)), torch.float64)
+        self.piece_ev, self.piece_end = [], []
+        # chunk metadata (offsets, label times) travels at the head of the train: a copy queued later on another stream
+        # would wait behind the whole train in the copy engine's queue
+        meta_np, time_np = FrontEnd._chunk_metadata(chunks)
+        if prev is not None and prev.meta_ev is not None:
+            prev.meta_ev.synchronize()           # the slot's previous upload has read the pinned staging buffers
+        h_meta = fe._buf(f"meta_host{slot}", (meta_np.size,), torch.int64, pinned=True)
+        h_time = fe._buf(f"time_host{slot}", (max(1, time_np.size),), torch.float64, pinned=True)
+        h_meta.numpy()[:] = meta_np
+        h_time.numpy()[: time_np.size] = time_np
+        self.d_meta = fe._buf(f"meta_dev{slot}", (meta_np.size,), torch.int64)
+        self.d_time = fe._buf(f"time_dev{slot}", (max(1, time_np.size),), torch.float64)
+        with torch.cuda.stream(fe.s_stage):
+            self.d_meta.copy_(h_meta, non_blocking=True)
+            self.d_time.copy_(h_time, non_blocking=True)
+            self.meta_ev = torch.cuda.Event()
+            self.meta_ev.record(fe.s_stage)
+        self.nbytes = self.n_samples * inp.audio.element_size() + self.n_evt * 24 + meta_np.nbytes + time_np.nbytes
+
+    def stage_until(self, c_goal: int) -> None:
+        """Enqueue piece copies until clip ``c_goal`` is covered (a few chunks ahead of the kernels that read them, so
+        the first chunk's kernels are not queued behind 45 copy calls)."""
+        fe, inp = self.fe, self.inp
+        c = self.piece_end[-1] if self.piece_end else 0
+        with torch.cuda.stream(fe.s_stage):
+            while c < min(c_goal, self.n_clips):
+                c_next = min(self.n_clips, c + fe.stage_piece_clips)
+                a0, a1 = int(self.clip_off[c]), int(self.clip_off[c_next])
+                if c == 0:
+                    fe._mark("h2d<", fe.s_stage, "copy")
+                self.audio[a0:a1].copy_(inp.audio[a0:a1], non_blocking=True)
+                if c == 0:                                        # all note events ride behind the first piece
+                    for j in range(3):
+                        self.events[j, :self.n_evt].copy_(inp.events[j, :self.n_evt], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(fe.s_stage)
+                self.piece_ev.append(e)
+                self.piece_end.append(c_next)
+                c = c_next
+                if c == self.n_clips:
+                    fe._mark("h2d>", fe.s_stage, "copy")
+
+    def event_for_clip_end(self, c1: int):
+        return self.piece_ev[int(np.searchsorted(np.asarray(self.piece_end), c1))]   # first piece ending at or after c1
+
+
 class FrontEnd:
     def __init__(self, recipe: CqtRecipe = CqtRecipe(), device: Optional[int] = None, engine: Optional[int] = None,
                  patch_mode: int = _lib.GTC_PATCH_VIT, img_size=(224, 224), chunk_segments: int = 19200,
@@ -93,6 +152,7 @@ class FrontEnd:
                 ops.set_option(_lib.GTC_OPT_PATCH_MAX_CTAS, (self.plan.sm_count - self.gemm_ctas) * int(patch_ctas_per_sm))
         with torch.cuda.device(self.device):
             self.s_copy, self.s_out, self.s_pre = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+            self.s_stage = torch.cuda.Stream()                        # whole-shard input staging; never joined by run()
             self.s_comp = torch.cuda.Stream(priority=-1)              # GEMM path: scheduled ahead of pending patch CTAs
             self.s_patch = torch.cuda.Stream(priority=0)
         self._bufs = {}
@@ -101,6 +161,9 @@ class FrontEnd:
         self._meta_plan, self._meta_ev, self._meta_sizes = None, None, None
         self.stage_bytes_limit = 4 << 30   # host-input shards up to this size are staged whole in HBM (else per-chunk double buffers)
         self.stage_piece_clips = 8         # clips per host->device copy of the staging train
+        self._stages = [None, None]        # staging slots: the current shard's and the prefetched next one's
+        self._stage_free = [None, None]    # event after which a slot's buffers are no longer read
+        self._stage_turn = 0
         self.trace = None              # set to a list to collect (label, stream name, event) marks: scripts/timeline.py
 
     # ------------------------------------------------------------------ host-side planning (integer arithmetic only)
@@ -133,6 +196,49 @@ class FrontEnd:
             chunks.append(ch)
         return chunks
 
+    @staticmethod
+    def _stage_key(inp: ShardInputs, chunks: List[_Chunk]):
+        return (inp.audio.data_ptr(), inp.audio.dtype, inp.events.data_ptr(), tuple((c.c0, c.c1, c.s1, c.e1) for c in chunks))
+
+    @staticmethod
+    def _chunk_metadata(chunks: List[_Chunk]):
+        meta_np = np.concatenate([np.concatenate([c.clip_off, c.seg_off, c.evt_off]) for c in chunks]).astype(np.int64) \
+            if chunks else np.zeros(1, np.int64)
+        time_np = np.concatenate([c.seg_time for c in chunks]) if chunks else np.zeros(1)
+        return meta_np, time_np
+
+    def _stage_slot_for(self, inp: ShardInputs, chunks: List[_Chunk], after_current_stream: bool) -> _Staging:
+        """The staging slot that holds (or is receiving) ``inp`` cut into ``chunks``; a new train is started when there
+        is none."""
+        key = self._stage_key(inp, chunks)
+        for st in self._stages:
+            if st is not None and st.key == key and not st.consumed:
+                return st
+        slot = self._stage_turn
+        self._stage_turn ^= 1
+        if self._stage_free[slot] is not None:
+            self.s_stage.wait_event(self._stage_free[slot])      # the run that last read this slot has finished
+        if after_current_stream:
+            self.s_stage.wait_stream(torch.cuda.current_stream())
+        st = _Staging(self, slot, inp, chunks, self._stages[slot])
+        self._stages[slot] = st
+        return st
+
+    def _stageable(self, inp: ShardInputs, chunks: List[_Chunk]) -> bool:
+        return bool(chunks) and chunks[-1].s1 * inp.audio.element_size() <= self.stage_bytes_limit
+
+    def prefetch(self, inp: ShardInputs, chunks: Optional[List[_Chunk]] = None) -> None:
+        """Start copying the NEXT shard's pinned host inputs (and its chunk metadata) into the other staging slot now, on
+        the staging stream: the copies run under the current shard's kernels and the next ``run(inp, chunks=chunks)``
+        finds its audio resident.  ``inp``'s host buffers must not change until that run.
+        (``run(..., next_inp=inp, next_chunks=chunks)`` calls this after its own copies are queued.)"""
+        chunks = self.plan_chunks(inp, ramp=True) if chunks is None else chunks
+        if not self._stageable(inp, chunks):
+            return
+        with torch.cuda.device(self.device):
+            st = self._stage_slot_for(inp, chunks, after_current_stream=False)
+            st.stage_until(st.n_clips)
+
     def _mark(self, label, stream, name):
         if self.trace is not None:
             e = torch.cuda.Event(enable_timing=True)
@@ -150,9 +256,12 @@ class FrontEnd:
 
     # ------------------------------------------------------------------ execution
     def run(self, inp: ShardInputs, device_inputs: bool = False, want_host_outputs: bool = True,
-            emit_patches: bool = True, consumer: Optional[Callable] = None, chunks: Optional[List[_Chunk]] = None) -> ShardOutputs:
+            emit_patches: bool = True, consumer: Optional[Callable] = None, chunks: Optional[List[_Chunk]] = None,
+            next_inp: Optional[ShardInputs] = None, next_chunks: Optional[List[_Chunk]] = None) -> ShardOutputs:
         """Process one shard.  ``consumer(patches, tabs_batch, first_segment_index)`` is called on the compute stream
-        for every patch batch (the training engine's input); without it patches are produced into a ring and dropped."""
+        for every patch batch (the training engine's input); without it patches are produced into a ring and dropped.
+        ``next_inp`` (host inputs): the shard the NEXT call will process; its host->device copies are queued behind this
+        shard's, so the copy engine runs on under this shard's last kernels (see ``prefetch``)."""
         plan, dev = self.plan, self.dev
         chunks = self.plan_chunks(inp, ramp=not device_inputs) if chunks is None else chunks
         n_seg = chunks[-1].g1 if chunks else 0
@@ -176,13 +285,16 @@ class FrontEnd:
         ev_ws = [None, None]                                                          # GEMM that last read ws2[b]
         pb = min(self.patch_batch, max(1, max_seg))
         ev_free = [[], []]
-        # all chunk metadata (offsets, label times) goes up in one copy from pinned memory; with device-resident inputs a
-        # chunk plan that is passed in again (same list object: epochs over the same shard) keeps its device copy
-        reuse_meta = device_inputs and self._meta_plan is not None and self._meta_plan is chunks
+        # host inputs: the whole shard is staged in HBM by ONE train of copies in pieces of a few clips (chunk metadata at
+        # its head), on a stream of its own and independent of the compute chunks (a 360-clip shard is 0.48 GB of int16
+        # PCM).  The copy engine never waits for a staging buffer to be released by a framing kernel, which with two
+        # per-chunk buffers it did whenever compute lagged (profiles/r01k_timeline_host.log).
+        staged = (not device_inputs) and self._stageable(inp, chunks)
+        # otherwise all chunk metadata (offsets, label times) goes up in one copy from pinned memory; with device-resident
+        # inputs a chunk plan that is passed in again (same list object: epochs over the same shard) keeps its device copy
+        reuse_meta = staged or (device_inputs and self._meta_plan is not None and self._meta_plan is chunks)
         if not reuse_meta:
-            meta_np = np.concatenate([np.concatenate([c.clip_off, c.seg_off, c.evt_off]) for c in chunks]).astype(np.int64) \
-                if chunks else np.zeros(1, np.int64)
-            time_np = np.concatenate([c.seg_time for c in chunks]) if chunks else np.zeros(1)
+            meta_np, time_np = self._chunk_metadata(chunks)
             if self._meta_ev is not None:
                 self._meta_ev.synchronize()      # the previous run's async upload has read the pinned staging buffers
             h_meta = self._buf("meta_host", (meta_np.size,), torch.int64, pinned=True)
@@ -190,8 +302,9 @@ class FrontEnd:
             h_meta.numpy()[:] = meta_np
             h_time.numpy()[: time_np.size] = time_np
             self._meta_sizes = (meta_np.size, max(1, time_np.size), meta_np.nbytes + time_np.nbytes)
-        d_meta_all = self._buf("meta_dev", (self._meta_sizes[0],), torch.int64)
-        d_time_all = self._buf("time_dev", (self._meta_sizes[1],), torch.float64)
+        if not staged:
+            d_meta_all = self._buf("meta_dev", (self._meta_sizes[0],), torch.int64)
+            d_time_all = self._buf("time_dev", (self._meta_sizes[1],), torch.float64)
         with torch.cuda.device(self.device):
             stats.zero_()
             self.s_copy.wait_stream(torch.cuda.current_stream())
@@ -206,8 +319,14 @@ class FrontEnd:
                     self._meta_ev = torch.cuda.Event()
                     self._meta_ev.record(self.s_copy)
                 self._meta_plan = chunks
-            if not device_inputs:
+            if not device_inputs and not staged:
                 out.h2d_bytes += self._meta_sizes[2]      # host-input runs upload their metadata every time
+            meta_ev = self._meta_ev
+            stage = None
+            if staged:
+                stage = self._stage_slot_for(inp, chunks, after_current_stream=True)
+                d_meta_all, d_time_all, meta_ev = stage.d_meta, stage.d_time, stage.meta_ev
+                out.h2d_bytes += stage.nbytes
             def emit(job, gate, s_p):
                 jb, jch, j_db, j_tabs, _ = job
                 jng = jch.g1 - jch.g0
@@ -232,44 +351,6 @@ class FrontEnd:
                     ev_p.record(s_p)
                 ev_free[jb].append(ev_p)
 
-            # ---- host inputs: the whole shard is staged in HBM by ONE train of copies in pieces of a few clips, issued
-            #      up front and independent of the compute chunks (a 360-clip shard is 0.48 GB of int16 PCM).  The copy
-            #      engine then never waits for a staging buffer to be released by a framing kernel, which with two
-            #      per-chunk buffers it did whenever compute lagged (profiles/r01k_timeline_host.log).
-            n_samples_all = chunks[-1].s1 if chunks else 0
-            n_evt_all = chunks[-1].e1 if chunks else 0
-            staged = (not device_inputs) and bool(chunks) and \
-                n_samples_all * inp.audio.element_size() <= self.stage_bytes_limit
-            piece_ev, piece_end = [], []
-            if staged:
-                clip_off_all = np.concatenate([[0], np.cumsum(np.asarray(inp.clip_lens, dtype=np.int64))])
-                d_audio_all = self._buf("audio_all", (n_samples_all,), inp.audio.dtype)
-                d_ev_all = self._buf("ev_all", (3, max(1, n_evt_all)), torch.float64)
-                n_clips_all = chunks[-1].c1
-                out.h2d_bytes += n_samples_all * inp.audio.element_size() + n_evt_all * 24
-
-                def stage_until(c_goal):
-                    """Enqueue staging copies until clip ``c_goal`` is covered (pieces are enqueued a few chunks ahead of
-                    the kernels that read them, so the first chunk's kernels are not queued behind 45 copy calls)."""
-                    c = piece_end[-1] if piece_end else 0
-                    with torch.cuda.stream(self.s_copy):
-                        while c < min(c_goal, n_clips_all):
-                            c_next = min(n_clips_all, c + self.stage_piece_clips)
-                            a0, a1 = int(clip_off_all[c]), int(clip_off_all[c_next])
-                            if c == 0:
-                                self._mark("h2d<", self.s_copy, "copy")
-                            d_audio_all[a0:a1].copy_(inp.audio[a0:a1], non_blocking=True)
-                            if c == 0:                                # all note events ride behind the first piece
-                                for j in range(3):
-                                    d_ev_all[j, :n_evt_all].copy_(inp.events[j, :n_evt_all], non_blocking=True)
-                            e = torch.cuda.Event()
-                            e.record(self.s_copy)
-                            piece_ev.append(e)
-                            piece_end.append(c_next)
-                            c = c_next
-                            if c == n_clips_all:
-                                self._mark("h2d>", self.s_copy, "copy")
-
             pending = None
             m_at = 0
             for k, ch in enumerate(chunks):
@@ -280,10 +361,10 @@ class FrontEnd:
                 d_time = d_time_all[ch.g0:ch.g1]
                 # ---- stage inputs
                 if staged:
-                    stage_until(chunks[min(k + 3, len(chunks) - 1)].c1)
-                    d_audio = d_audio_all[ch.s0:ch.s1]
-                    d_on, d_du, d_pi = d_ev_all[0, ch.e0:ch.e1], d_ev_all[1, ch.e0:ch.e1], d_ev_all[2, ch.e0:ch.e1]
-                    ev_h2d = piece_ev[int(np.searchsorted(np.asarray(piece_end), ch.c1))]     # first piece that ends at or after clip c1
+                    stage.stage_until(chunks[min(k + 3, len(chunks) - 1)].c1)
+                    d_audio = stage.audio[ch.s0:ch.s1]
+                    d_on, d_du, d_pi = (stage.events[j, ch.e0:ch.e1] for j in range(3))
+                    ev_h2d = stage.event_for_clip_end(ch.c1)
                 else:
                   with torch.cuda.stream(self.s_copy):
                     if ev_pre[b] is not None:
@@ -306,6 +387,8 @@ class FrontEnd:
                     ev_h2d.record(self.s_copy)
                 with torch.cuda.stream(self.s_pre):
                     self.s_pre.wait_event(ev_h2d)
+                    if meta_ev is not None:
+                        self.s_pre.wait_event(meta_ev)                # chunk offsets / label times
                     d_clip_off, d_seg_off, d_evt_off = d_meta[: nc + 1], d_meta[nc + 1: 2 * nc + 2], d_meta[2 * nc + 2:]
                     d_db = out.db[ch.g0:ch.g1] if not host_out else self._buf(f"db{b}", (max_seg, nb, T), torch.float32)[:ng]
                     d_tabs = out.tabs[ch.g0:ch.g1] if not host_out else self._buf(f"tabs{b}", (max_seg, 6, 19), torch.int8)[:ng]
@@ -387,6 +470,14 @@ class FrontEnd:
             torch.cuda.current_stream().wait_stream(self.s_copy)
             torch.cuda.current_stream().wait_stream(self.s_pre)
             torch.cuda.current_stream().wait_stream(self.s_patch)
+            if stage is not None:
+                # every kernel that read this slot is ordered before this point of the current stream; the staging
+                # stream itself is NOT joined, so a prefetch of the next shard keeps copying past the end of this call
+                stage.consumed = True
+                self._stage_free[stage.slot] = torch.cuda.Event()
+                self._stage_free[stage.slot].record(torch.cuda.current_stream())
+            if next_inp is not None and not device_inputs:
+                self.prefetch(next_inp, next_chunks)
         self._last_stats = (stats, self._bufs.get(("stats_host", True)) if host_out else None)
         return out
 
