@@ -271,7 +271,8 @@ def run_cuda_arm(args):
     inp_dev = ShardInputs(audio_dev, lens, events_dev, evt_off, sr=SR)
     inp_host = ShardInputs(audio_host, lens, events_host, evt_off, sr=SR)
     chunks = fe.plan_chunks(inp_dev)
-    chunks_host = fe.plan_chunks(inp_host, ramp=not args.no_ramp)     # small first/last chunks: short pipeline fill and drain
+    chunks_host = fe.plan_chunks(inp_host, ramp=not args.no_ramp)     # small first chunks: short pipeline fill
+    chunks_flat_host = fe.plan_chunks(inp_host, ramp=False)
     seconds_per_step = n_clips * CLIP_SECONDS
     stats_vec = torch.zeros(8, dtype=torch.int64, device=dev)
 
@@ -279,11 +280,16 @@ def run_cuda_arm(args):
     # PAGEABLE host memory, which synchronises the stream first -- one hidden host sync per step.)
     stats_head = torch.tensor([n_clips, 0, int(lens.sum())], dtype=torch.int64).pin_memory()
 
-    def step(inp, device_inputs, last=False):
+    def step(inp, device_inputs, last=False, first=False):
         # host-input arm: the next step's shard (the same pinned buffers stand in for it) is prefetched behind this
         # step's copies, as a training loop would do with the next shard of the corpus; the last step prefetches nothing
-        out = fe.run(inp, device_inputs=device_inputs, chunks=chunks if device_inputs else chunks_host,
-                     next_inp=inp if (args.prefetch and not device_inputs and not last) else None, next_chunks=chunks_host)
+        # a cold step ramps its chunks up from 15 clips (its audio is still on the bus); a prefetched step finds ~90 clips
+        # resident and uses the same full-wave chunks as the device-resident arm
+        pref = args.prefetch and not device_inputs
+        mine = chunks if device_inputs else (chunks_flat_host if (pref and not first and args.flat_after_first) else chunks_host)
+        nxt = chunks_flat_host if args.flat_after_first else chunks_host
+        out = fe.run(inp, device_inputs=device_inputs, chunks=mine,
+                     next_inp=inp if (pref and not last) else None, next_chunks=nxt)
         # tiny per-shard stats gather (the path's only collective), jam_to_tablature.py:376-378
         stats_head[1] = out.n_seg
         stats_vec[:3].copy_(stats_head, non_blocking=True)
@@ -299,7 +305,7 @@ def run_cuda_arm(args):
 
     def timed(inp, device_inputs, steps, warmup):
         for _ in range(warmup):
-            step(inp, device_inputs, last=True)       # warm-up steps prefetch nothing: the timed region starts cold
+            step(inp, device_inputs, last=True, first=True)   # warm-up steps prefetch nothing: the timed region starts cold
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         fe.patch_events = [] if device_inputs else None      # per-launch CUDA events on the launching stream, timed region only
@@ -308,7 +314,7 @@ def run_cuda_arm(args):
         out = None
         t_host = time.perf_counter()
         for i in range(steps):
-            out = step(inp, device_inputs, last=(i == steps - 1))
+            out = step(inp, device_inputs, last=(i == steps - 1), first=(i == 0))
         timed.host_ms = 1e3 * (time.perf_counter() - t_host) / max(1, steps)     # CPU time to enqueue one step
         e1.record()
         barrier()
@@ -427,6 +433,7 @@ def main():
     ap.add_argument("--coresident", action="store_true", help="experiment: patch kernels on their own stream under the next chunk GEMM (needs -DTC_MAXNREG=152; slower, see profiles/r01j_coresident.md)")
     ap.add_argument("--no-wave-aware", action="store_true", help="plain greedy chunks (largest that fit) instead of full GEMM tile waves")
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false", help="e2e arm: do not start the next step's host->device copies under the current step")
+    ap.add_argument("--ramp-always", dest="flat_after_first", action="store_false", help="e2e arm: prefetched steps also use the ramped chunk plan of a cold step")
     ap.add_argument("--numa-bind", action="store_true", help="bind each rank to the CPUs local to its GPU before allocating pinned memory")
     ap.add_argument("--clock-period", type=float, default=0.02, help="seconds between NVML clock samples during the timed region (0 = off)")
     ap.add_argument("--opt", action="append", default=[], help="library option id=value (gtc_set_option), for experiments")
