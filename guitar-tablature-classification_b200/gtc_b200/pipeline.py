@@ -4,9 +4,11 @@ This is the index-aligned in-memory path: clip ``c`` yields ``n
 (cqt.py:26-45), one label per segment at ``t_i = (i + 0.5) * duration / n_seg`` (jam_to_tablature.py:273-274 with
 ``num_images = n_seg``) and one (3, H, W) patch per segment (ViT_dataloader.py:27-51 or the CNN contract).
 
-Clips are processed in chunks on three CUDA streams so that the host->device copy of chunk k+1 and the
-device->host copy of chunk k-1 overlap the kernels of chunk k.  With ``device_inputs=True`` the audio/events are
-already resident in HBM and no copies are issued (the kernel-only number of bench.py).
+Clips are processed in chunks of whole clips (gtc_b200/chunks.py: each chunk fills whole waves of GEMM tiles).  Streams:
+``s_stage`` host->device staging of whole shards (two slots; never joined, so the next shard can be prefetched under the
+current one), ``s_pre`` framing + label rasterisation (beside the previous chunk's GEMM), ``s_comp`` GEMM -> dB finish ->
+patches back to back, ``s_out`` device->host copies of features and labels.  With ``device_inputs=True`` the audio and
+events are already resident in HBM and no copies are issued (the kernel-only number of bench.py).  DESIGN.md section 4.
 """
 from __future__ import annotations
 
