@@ -89,8 +89,8 @@ int gtc_cqt_segments_db(const gtc_plan* plan, const float* d_audio, const int64_
                         float power, float amin, float top_db, float cut_db, float floor_db,
                         gtc_stream_t stream);
 /* The two stages of gtc_cqt_segments_db as separate calls (same workspace, same stream order), so that a caller can
- * put an event between the framing kernel and the tensor-core contraction: the pipeline uses it to start the previous
- * chunk's patch kernel exactly when the next GEMM becomes runnable, so the two share the GPU. */
+ * run them on different streams: the pipeline frames chunk k+1 beside the tensor-core contraction of chunk k and keeps
+ * GEMM -> finish -> patches of one chunk back to back on the compute stream (gtc_b200/pipeline.py). */
 int gtc_cqt_frame(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off, const int64_t* d_seg_off,
                   int64_t n_clips, int64_t n_seg, void* d_workspace, size_t workspace_bytes, gtc_stream_t stream);
 /* gtc_cqt_frame for the WAV file's own 16-bit PCM samples (mono, already channel-averaged if needed): the kernel converts
@@ -103,7 +103,8 @@ int gtc_cqt_contract_db(const gtc_plan* plan, const int64_t* d_clip_off, const i
                         float power, float amin, float top_db, float cut_db, float floor_db, gtc_stream_t stream);
 /* process-wide tunables */
 #define GTC_OPT_PATCH_MAX_CTAS 16  /* grid limit of the patch kernel (0 = SMs x resident CTAs) */
-#define GTC_OPT_PATCH_CTAS_PER_SM 17 /* resident patch CTAs per SM (default 2: measured fastest on B200; 0 restores the default) */
+#define GTC_OPT_PATCH_CTAS_PER_SM 17 /* resident patch CTAs per SM (default 2: measured fastest on B200; 0 restores the default).  The launch
+                                       requests 228 KB / k of shared memory so that exactly k CTAs fit and the persistent grid is placed evenly */
 int gtc_set_option(int option, int value);
 
 /* Same contraction, complex output before |.|: d_out_c [n_seg, n_bins, n_frames, 2] fp32 (== librosa.cqt). */
