@@ -89,6 +89,9 @@ class _Staging:
         h_time.numpy()[: time_np.size] = time_np
         self.d_meta = fe._buf(f"meta_dev{slot}", (meta_np.size,), torch.int64)
         self.d_time = fe._buf(f"time_dev{slot}", (max(1, time_np.size),), torch.float64)
+        # the staging stream is never joined into the caller's stream: tell the caching allocator who else uses the blocks
+        for t in (self.audio, self.events, self.d_meta, self.d_time):
+            t.record_stream(fe.s_stage)
         with torch.cuda.stream(fe.s_stage):
             self.d_meta.copy_(h_meta, non_blocking=True)
             self.d_time.copy_(h_time, non_blocking=True)
