@@ -106,7 +106,7 @@ extern "C" int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int 
   const bool half = gemm_engine == GTC_GEMM_TCGEN05_FP16X2;
   const bool tensor = gemm_engine != GTC_GEMM_SIMT_FP32;
   p.elem_bytes = half ? 2 : 4;
-  p.kb_elems = 128 / p.elem_bytes;
+  p.kb_elems = (tensor ? TC_KB_BYTES : 128) / p.elem_bytes;
   p.x_scale = half ? 256.f : 1.f;                       // |x| < 256 stays finite in fp16; lo part normal down to |x| ~ 1e-3
   p.out_scale = 1.f;
   p.kp = (int)round_up(p.row_len, p.kb_elems);

@@ -18,10 +18,12 @@
 namespace gtc {
 
 constexpr int TBM = 128;             // rows per tile (UMMA M)
-constexpr int TBK = 32;              // fp32 per k-block = 128 bytes = one swizzle row
+constexpr int TKB_BYTES = TC_KB_BYTES;   // bytes of K per k-block = one swizzle row (128 or 64)
+static_assert(TKB_BYTES == 128 || TKB_BYTES == 64, "k-block rows are one 128-byte or 64-byte swizzle row");
+constexpr int TBK = TKB_BYTES / 4;   // fp32 per k-block
 constexpr int TMAXN = 256;           // max operator rows per tile (UMMA N)
-constexpr int TSTAGES = 2;
-constexpr int TUMMA_K = 8;           // tf32
+constexpr int TSTAGES = TC_STAGES;
+constexpr int TUMMA_K = 8;           // tf32 per MMA = 32 bytes of K (16 fp16)
 constexpr uint32_t X_TILE_BYTES = TBM * TBK * 4;        // 16 KB
 constexpr uint32_t OP_TILE_BYTES = TMAXN * TBK * 4;     // 32 KB (NC rows used)
 constexpr uint32_t STAGE_BYTES = 2 * X_TILE_BYTES + 2 * OP_TILE_BYTES;   // 96 KB
@@ -112,14 +114,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+// K-major operand tile, 128- or 64-byte swizzle: rows of TKB_BYTES, 8-row groups 8 * TKB_BYTES apart
+// (cute::UMMA::SmemDescriptor; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);          // start address  [0,14)
   d |= (uint64_t)1 << 16;                               // leading byte offset (ignored for swizzled K-major) [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset = 8 rows * 128 B              [32,46)
+  d |= (uint64_t)((8 * TKB_BYTES) >> 4) << 32;          // stride byte offset = 8 rows                      [32,46)
   d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)                      [46,48)
-  d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B                         [61,64)
+  d |= (uint64_t)(TKB_BYTES == 128 ? 2 : 4) << 61;      // layout type                                      [61,64)
   return d;
 }
 // cute::UMMA::InstrDescriptor : c=F32, a=b=fmt (0 = F16, 2 = TF32), both K-major, N>>3 at [17,23), M>>4 at [24,29)
@@ -153,7 +156,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo,
                const TcParams prm) {
   constexpr int H = NC / 2;                  // columns per epilogue warp
-  constexpr int EPK = kHalf ? 64 : 32;       // operand elements per k-block
+  constexpr int EPK = TKB_BYTES / (kHalf ? 2 : 4);   // operand elements per k-block
   static_assert(NC % 16 == 0 && NC <= TMAXN && H % 8 == 0, "unsupported tile width");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bars[2 * TSTAGES + 4];
@@ -411,11 +414,11 @@ static int encode_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t 
   if (!fn) return GTC_E_CUDA;
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {cols * (uint64_t)elem_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_rows};          // 128-byte swizzle row
+  cuuint32_t box[2] = {(cuuint32_t)(TKB_BYTES / elem_bytes), box_rows};    // one swizzle row of K
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, TKB_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GTC_REQUIRE(r == CUDA_SUCCESS, GTC_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return GTC_OK;
@@ -483,7 +486,7 @@ int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int6
   if (rc != GTC_OK) return rc;
   TcParams prm;
   prm.nc = pick_nc(p.n_out);
-  prm.kb_per_split = p.tc_kb_per_split > 0 ? p.tc_kb_per_split : 8;
+  prm.kb_per_split = (p.tc_kb_per_split > 0 ? p.tc_kb_per_split : 8) * (128 / TKB_BYTES);   // option counts 128-byte blocks
   prm.n_chunks = (int)ceil_div(p.n_out, prm.nc);
   prm.n_out = p.n_out;
   prm.kb_per_part = p.kp / p.kb_elems;

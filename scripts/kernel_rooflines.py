@@ -39,7 +39,7 @@ n_seg = int(seg_off[-1]); n_rows = n_seg + n_clips * (plan.parts - 1)
 co, so = torch.from_numpy(clip_off).to(dev), torch.from_numpy(seg_off).to(dev)
 ws = plan.workspace(n_seg, n_clips)
 db = torch.empty((n_seg, 96, 5), device=dev)
-kp = 2240                                                     # fp16 operand row: 2205 samples padded to a 128-byte multiple
+kp = 2208                                                     # fp16 operand row: 2205 samples padded to a 64-byte multiple
 rows_alloc = n_rows + 128
 ms = timeit(lambda: plan.frame(audio, co, so, n_seg, ws))
 hbm_row("frame_kernel<half,float>", ms, n_rows * 2205 * 4 + 2 * rows_alloc * kp * 2, "fp32 audio in, fp16 hi+lo rows out")
