@@ -19,7 +19,7 @@ namespace gtc {
 
 constexpr int TBM = 128;             // rows per tile (UMMA M)
 constexpr int TKB_BYTES = TC_KB_BYTES;   // bytes of K per k-block = one swizzle row (128 or 64)
-static_assert(TKB_BYTES == 128 || TKB_BYTES == 64, "k-block rows are one 128-byte or 64-byte swizzle row");
+static_assert(TKB_BYTES == 128 || TKB_BYTES == 64 || TKB_BYTES == 32, "k-block rows are one 128-, 64- or 32-byte swizzle row");
 constexpr int TBK = TKB_BYTES / 4;   // fp32 per k-block
 constexpr int TMAXN = 256;           // max operator rows per tile (UMMA N)
 constexpr int TSTAGES = TC_STAGES;
@@ -115,14 +115,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile, 128- or 64-byte swizzle: rows of TKB_BYTES, 8-row groups 8 * TKB_BYTES apart
-// (cute::UMMA::SmemDescriptor; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+// (cute::UMMA::SmemDescriptor; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B)
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);          // start address  [0,14)
   d |= (uint64_t)1 << 16;                               // leading byte offset (ignored for swizzled K-major) [16,30)
   d |= (uint64_t)((8 * TKB_BYTES) >> 4) << 32;          // stride byte offset = 8 rows                      [32,46)
   d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)                      [46,48)
-  d |= (uint64_t)(TKB_BYTES == 128 ? 2 : 4) << 61;      // layout type                                      [61,64)
+  d |= (uint64_t)(TKB_BYTES == 128 ? 2 : TKB_BYTES == 64 ? 4 : 6) << 61;   // layout type                   [61,64)
   return d;
 }
 // cute::UMMA::InstrDescriptor : c=F32, a=b=fmt (0 = F16, 2 = TF32), both K-major, N>>3 at [17,23), M>>4 at [24,29)
@@ -418,7 +418,7 @@ static int encode_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t 
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, TKB_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, TKB_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : TKB_BYTES == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GTC_REQUIRE(r == CUDA_SUCCESS, GTC_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return GTC_OK;

@@ -9,12 +9,13 @@
 // tcgen05 engines: bytes of K per operand row and shared-memory stage (one swizzle row), and ring depth.  128 B x 2 stages
 // and 64 B x 4 stages hold the same 184 KB in flight; the finer ring refills a slot after half as many MMAs, so a TMA
 // round trip has three stages of MMA work to hide under instead of one.  Measured on B200 (scripts/gemm_bench.py, same
-// box, GTC_LIB_PATH A/B): GEMM + finish of an 18 900-row chunk 0.351 -> 0.319 ms, step 11.59 -> 11.41 ms.  64 is the default.
+// box, GTC_LIB_PATH A/B): GEMM + finish of an 18 900-row chunk 0.351 -> 0.319 ms, step 11.59 -> 11.41 ms.  64 is the default;
+// 32 B x 8 stages (one MMA k-step per stage) is correct but TMA-request-bound: 0.515 ms.
 #ifndef TC_KB_BYTES
 #define TC_KB_BYTES 64
 #endif
 #ifndef TC_STAGES
-#define TC_STAGES (TC_KB_BYTES == 128 ? 2 : 4)
+#define TC_STAGES (256 / TC_KB_BYTES)
 #endif
 
 namespace gtc {
