@@ -9,11 +9,12 @@ n = 18837
 db = (torch.rand((n, 96, 5), device=dev) * 120 - 120)
 out = torch.empty((n, 3, 224, 224), device=dev)
 byts = n * (3 * 224 * 224 * 4 + 1920)
+if os.environ.get('PATCH_CTAS'): ops.set_option(17, int(os.environ['PATCH_CTAS']))
 for _ in range(3): ops.patches(db, out=out)
 torch.cuda.synchronize()
 ts = []
 for _ in range(15):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); ops.patches(db, out=out); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
-print(json.dumps({"lib": os.environ.get("GTC_LIB_PATH", "libgtc.so").split("/")[-1], "ms_med": round(float(np.median(ts)), 4),
+print(json.dumps({"lib": os.environ.get("GTC_LIB_PATH", "libgtc.so").split("/")[-1], "ctas_per_sm": os.environ.get("PATCH_CTAS", "default"), "ms_med": round(float(np.median(ts)), 4),
                   "ms_min": round(min(ts), 4), "GBs_med": round(byts / np.median(ts) / 1e6, 1)}))
