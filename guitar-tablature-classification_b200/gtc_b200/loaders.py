@@ -118,6 +118,20 @@ def random_split(dataset, lengths, generator=None) -> List[Subset]:
     return out
 
 
+def sampler_order(n: int, shuffle: bool) -> torch.Tensor:
+    """Item order of one epoch exactly as torch's DataLoader produces it, consuming the global CPU generator the same way
+    (torch/utils/data/dataloader.py): creating the iterator draws the workers' base seed, then RandomSampler.__iter__ draws
+    its own seed and permutes with a private generator.  Under ``torch.manual_seed(s)`` the batches therefore come in the
+    order the reference's ``DataLoader(..., shuffle=True)`` (my_dataloader.py:62, ViT_dataloader.py:74) yields them."""
+    torch.empty((), dtype=torch.int64).random_()                       # _BaseDataLoaderIter.__init__: base seed
+    if not shuffle:
+        return torch.arange(n, dtype=torch.int64)
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())    # RandomSampler.__iter__
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return torch.randperm(n, generator=g)
+
+
 class DeviceLoader:
     """Iterable of device batches over a Subset.  Replaces DataLoader(batch_size, shuffle, num_workers, pin_memory)."""
 
@@ -137,7 +151,7 @@ class DeviceLoader:
 
     def __iter__(self):
         n = self._index.numel()
-        order = self._index[torch.randperm(n, device=self._index.device)] if self.shuffle else self._index
+        order = self._index[sampler_order(n, self.shuffle).to(self._index.device)]
         for b in range(len(self)):
             idx = order[b * self.batch_size: (b + 1) * self.batch_size].contiguous()
             yield self._base.batch(idx)

@@ -214,3 +214,29 @@ def test_chunk_planner_properties():
     assert ck.plan_bounds([], 100) == [] and ck.plan_bounds([7], 100) == [(0, 1)]
     # tile widths follow cqt_gemm_tc.cu: 960 -> 240, 840*... ragged -> 256
     assert ck.gemm_tiles(128, 0, 1, 960) == 4 and ck.gemm_tiles(129, 0, 1, 960) == 8 and ck.gemm_tiles(128, 0, 1, 2 * 84 * 130) == -(-21840 // 240)
+
+
+def test_loader_epoch_order_equals_torch_dataloader():
+    """gtc_b200.loaders.sampler_order reproduces the item order (and the global-RNG consumption) of the reference's
+    DataLoader(shuffle=True / False) under torch.manual_seed, over several epochs and for the worker counts the
+    reference uses (my_dataloader.py:62-70, ViT_dataloader.py:74-86)."""
+    import torch
+    from torch.utils.data import DataLoader, Dataset
+    from gtc_b200.loaders import sampler_order
+
+    class Items(Dataset):
+        def __len__(self):
+            return 53
+
+        def __getitem__(self, i):
+            return i
+
+    for workers in (0, 2):
+        for shuffle in (True, False):
+            torch.manual_seed(1234)
+            dl = DataLoader(Items(), batch_size=8, shuffle=shuffle, num_workers=workers)
+            ref = [torch.cat([b for b in dl]).tolist() for _ in range(3)]
+            ref_next = torch.rand(1).item()                         # the global generator is left in the same state
+            torch.manual_seed(1234)
+            got = [sampler_order(53, shuffle).tolist() for _ in range(3)]
+            assert got == ref and torch.rand(1).item() == ref_next
