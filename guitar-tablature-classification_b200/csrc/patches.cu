@@ -225,6 +225,38 @@ patch_kernel(const PatchParams p) {
   }
 }
 
+// ToTensor + Normalize of decoded, resized RGB pictures (my_dataloader.py:19-20), gathered by the sampler's index.
+// One thread = four pixels of one row: 12 input bytes (HWC) -> one float4 per channel plane (CHW).  x / 255, - mean, / std
+// are the three separately rounded fp32 operations torchvision performs (tensor.div(255); sub_(mean); div_(std)).
+__global__ void __launch_bounds__(256)
+rgb8_normalize_kernel(const uint8_t* __restrict__ rgb, const int64_t* __restrict__ index, int64_t n, int h, int w,
+                      float3 mean, float3 stdv, float* __restrict__ out) {
+  const int wq = w >> 2;
+  const int64_t quads_per_item = (int64_t)h * wq;
+  const int64_t total = n * quads_per_item;
+  const int64_t plane = (int64_t)h * w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t item = i / quads_per_item;
+    const int64_t q = i - item * quads_per_item;                       // quad within the picture (row-major)
+    const int64_t src = index ? __ldg(index + item) : item;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(rgb + (src * plane + q * 4) * 3);
+    const uint32_t w0 = __ldcs(p), w1 = __ldcs(p + 1), w2 = __ldcs(p + 2);     // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+    const uint8_t b[12] = {(uint8_t)w0, (uint8_t)(w0 >> 8), (uint8_t)(w0 >> 16), (uint8_t)(w0 >> 24),
+                           (uint8_t)w1, (uint8_t)(w1 >> 8), (uint8_t)(w1 >> 16), (uint8_t)(w1 >> 24),
+                           (uint8_t)w2, (uint8_t)(w2 >> 8), (uint8_t)(w2 >> 16), (uint8_t)(w2 >> 24)};
+    const float m[3] = {mean.x, mean.y, mean.z}, s[3] = {stdv.x, stdv.y, stdv.z};
+    float* dst = out + item * 3 * plane + q * 4;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        v[j] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)b[3 * j + c], 255.f), m[c]), s[c]);
+      __stcs(reinterpret_cast<float4*>(dst + c * plane), make_float4(v[0], v[1], v[2], v[3]));
+    }
+  }
+}
+
 // tickets: a small ring of counters owned by the library; each launch zeroes and uses the next slot on its stream
 constexpr int kTicketSlots = 1024;
 __device__ unsigned int g_patch_tickets[kTicketSlots];
@@ -304,4 +336,26 @@ extern "C" int gtc_patches(const float* d_db, const int64_t* d_index, int64_t n,
   if (fast && n_frames == 5) return launch(patch_kernel<5>);
   if (fast && n_frames == 9) return launch(patch_kernel<9>);
   return launch(patch_kernel<0>);
+}
+
+extern "C" int gtc_patches_rgb8(const uint8_t* d_rgb, const int64_t* d_index, int64_t n, int h, int w, float mean_r,
+                                float mean_g, float mean_b, float std_r, float std_g, float std_b, float* d_out,
+                                gtc_stream_t stream) {
+  GTC_REQUIRE(n >= 0, GTC_E_ARG, "gtc_patches_rgb8: negative n");
+  if (n == 0) return GTC_OK;
+  GTC_REQUIRE(d_rgb && d_out, GTC_E_ARG, "gtc_patches_rgb8: null pointer");
+  GTC_REQUIRE(h > 0 && w > 0 && w % 4 == 0, GTC_E_ARG, "gtc_patches_rgb8: w must be a positive multiple of 4 (got %d x %d)", h, w);
+  GTC_REQUIRE((reinterpret_cast<uintptr_t>(d_rgb) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0, GTC_E_ARG,
+              "gtc_patches_rgb8: d_rgb must be 4-byte and d_out 16-byte aligned");
+  GTC_REQUIRE(std_r != 0.f && std_g != 0.f && std_b != 0.f, GTC_E_ARG, "gtc_patches_rgb8: zero std");
+  int sms = sm_count_of_current_device();
+  if (sms <= 0) return GTC_E_CUDA;
+  const int64_t total = n * h * (int64_t)(w / 4);
+  int64_t blocks = ceil_div(total, 256);
+  if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+  rgb8_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_rgb, d_index, n, h, w,
+                                                                            make_float3(mean_r, mean_g, mean_b),
+                                                                            make_float3(std_r, std_g, std_b), d_out);
+  GTC_CUDA_CHECK(cudaGetLastError());
+  return GTC_OK;
 }

@@ -56,6 +56,7 @@ PROTOTYPES = {
     "gtc_augment_batch": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f, C.c_uint64, _i, _f, _vp]),
     "gtc_db_normalize": (_i, [_vp, _i64, _f, _vp, _vp]),
     "gtc_patches": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp]),
+    "gtc_patches_rgb8": (_i, [_vp, _vp, _i64, _i, _i, _f, _f, _f, _f, _f, _f, _vp, _vp]),
 }
 
 

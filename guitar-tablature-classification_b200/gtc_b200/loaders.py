@@ -53,6 +53,25 @@ def load_feature_dir(audio_dir: str, suffix: str = ".npy"):
     return names, (np.stack(arrs) if arrs else np.zeros((0, 96, 5), np.float32))
 
 
+def load_png_dir(audio_dir: str, size=(224, 224), workers: int = 8):
+    """The picture route of my_dataloader.py: every ``.png`` of ``audio_dir`` in sorted order (:10), decoded to RGB (:29) and
+    resized by PIL exactly as ``transforms.Resize((224, 224))`` does for a PIL image (bilinear, PIL's own antialiasing;
+    :18).  Decode and resize stay on the host -- they are the reference's own library calls -- and run ONCE per dataset
+    (the reference repeats them every epoch); the result is [N, H, W, 3] uint8, 150 KB per item."""
+    from concurrent.futures import ThreadPoolExecutor
+    from PIL import Image
+    names = sorted(f for f in os.listdir(audio_dir) if f.endswith('.png'))
+    out = np.empty((len(names), size[0], size[1], 3), dtype=np.uint8)
+
+    def one(i):
+        with Image.open(os.path.join(audio_dir, names[i])) as im:
+            out[i] = np.asarray(im.convert("RGB").resize((size[1], size[0]), Image.BILINEAR))
+
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
+        list(ex.map(one, range(len(names))))
+    return names, out
+
+
 def load_label_dir(annotation_dir: str):
     names, arrs = _load_dir(annotation_dir, ".npy")
     for f, a in zip(names, arrs):
@@ -68,6 +87,7 @@ class DeviceTabDataset:
                  audio_files: Optional[List[str]] = None, annotation_files: Optional[List[str]] = None):
         assert db.shape[0] == tabs.shape[0], "Mismatch in audio and annotation file counts."
         self.db, self.tabs = db.contiguous(), tabs.contiguous()
+        self.rgb = None                 # [N, H, W, 3] uint8 when the dataset was built from pictures (my_dataloader)
         self.mode, self.img_size, self.label_kind = mode, tuple(img_size), label_kind
         self.audio_files, self.annotation_files = audio_files or [], annotation_files or []
 
@@ -76,7 +96,10 @@ class DeviceTabDataset:
 
     def batch(self, index: torch.Tensor):
         """index int64 [B] (device) -> (inputs [B,3,H,W] fp32, labels) assembled on the current stream."""
-        x = ops.patches(self.db, index=index, img_size=self.img_size, mode=self.mode)
+        if self.rgb is not None:                                   # picture route: ToTensor + Normalize of decoded PNGs
+            x = ops.patches_rgb8(self.rgb, index=index)
+        else:
+            x = ops.patches(self.db, index=index, img_size=self.img_size, mode=self.mode)
         if self.label_kind == "argmax":
             y = ops.labels_argmax(self.tabs, index)                # (B, 6) int64       my_dataloader.py:40-44
         else:

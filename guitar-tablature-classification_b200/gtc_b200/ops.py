@@ -324,3 +324,23 @@ def patches(db: torch.Tensor, index: Optional[torch.Tensor] = None, img_size=(22
     _lib.check(_lib.load().gtc_patches(_ptr(db), _ptr(index), n, db.shape[1], db.shape[2], h, w, int(mode), _ptr(out),
                                        _stream()), "gtc_patches")
     return out
+
+
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)        # my_dataloader.py:20
+
+
+def patches_rgb8(rgb: torch.Tensor, index: Optional[torch.Tensor] = None, mean=IMAGENET_MEAN, std=IMAGENET_STD,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """rgb [n_total, H, W, 3] uint8 (decoded + resized pictures, PIL's byte order) -> [n, 3, H, W] fp32
+    ((x / 255) - mean) / std : ToTensor + Normalize of my_dataloader.py:19-20, bit for bit."""
+    _need_cuda(rgb, index)
+    assert rgb.dtype == torch.uint8 and rgb.dim() == 4 and rgb.shape[3] == 3 and rgb.is_contiguous()
+    n = rgb.shape[0] if index is None else index.numel()
+    if index is not None:
+        assert index.dtype == torch.int64
+    h, w = int(rgb.shape[1]), int(rgb.shape[2])
+    if out is None:
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=rgb.device)
+    _lib.check(_lib.load().gtc_patches_rgb8(_ptr(rgb), _ptr(index), n, h, w, *[float(v) for v in mean], *[float(v) for v in std],
+                                            _ptr(out), _stream()), "gtc_patches_rgb8")
+    return out

@@ -6,11 +6,17 @@ batches assembled on the GPU by libgtc (reference /root/reference/my_dataloader.
 
 Tensor contract handed to bestengine.py:899-920: ``inputs (B,3,224,224) fp32`` ImageNet-normalised with the reference's
 mean/std (:20) and ``labels (B,6) int64`` = argmax over the 19 frets of each string (first 1 wins, all-zero row -> 0,
-:40-44).  The reference reads matplotlib PNG pictures (:10,:29); the picture rendering is not a numeric contract
-(SURVEY.md 8g.11), so ``audio_dir`` holds the (96, T) dB feature ``.npy`` files instead and the "picture" is the grey
-image clip((dB+120)/120, 0, 1) with the highest bin on the top row, resized bilinearly (what transforms.Resize does when
-up-sampling) to 224x224 and replicated to 3 channels.  The split is unseeded like the reference's (:60).
+:40-44).  Two kinds of ``audio_dir``:
+* ``.png`` pictures, the reference's own input (:10,:29): decoded and resized by PIL on the host exactly as the reference
+  does (once per dataset instead of once per item and epoch), ToTensor + Normalize per batch on the GPU -- the batches
+  are bit-identical to the reference's (tests/test_gpu_dropins.py compares with torchvision's own transform).
+* (96, T) dB feature ``.npy`` files (what this repo's cqt.py writes): rendering the pictures is matplotlib's business and
+  not a numeric contract, so here the "picture" is the grey image clip((dB+120)/120, 0, 1) with the
+  highest bin on the top row, resized bilinearly to 224x224 and replicated to 3 channels.
+The split is unseeded like the reference's (:60).
 """
+import os
+
 import torch
 
 from gtc_b200 import _lib, loaders
@@ -19,11 +25,20 @@ from gtc_b200 import _lib, loaders
 class GuitarTabDataset(loaders.DeviceTabDataset):
     def __init__(self, audio_dir, annotation_dir):
         dev = loaders._device()
-        audio_files, db = loaders.load_feature_dir(audio_dir, ".npy")
         annotation_files, tabs = loaders.load_label_dir(annotation_dir)
-        assert len(audio_files) == len(annotation_files), "Mismatch in audio and annotation file counts."
-        super().__init__(torch.from_numpy(db).to(dev), torch.from_numpy(tabs).to(dev), _lib.GTC_PATCH_CNN, (224, 224),
-                         label_kind="argmax", audio_files=audio_files, annotation_files=annotation_files)
+        if any(f.endswith('.png') for f in os.listdir(audio_dir)):
+            # the reference's own input (my_dataloader.py:10): pictures rendered by new_cqt.py.  PIL decode + resize on
+            # the host once, then ToTensor + Normalize per batch on the GPU -- bit-identical to the reference's transform
+            audio_files, rgb = loaders.load_png_dir(audio_dir)
+            assert len(audio_files) == len(annotation_files), "Mismatch in audio and annotation file counts."
+            super().__init__(torch.zeros((len(audio_files), 1, 1), device=dev), torch.from_numpy(tabs).to(dev), _lib.GTC_PATCH_CNN,
+                             (224, 224), label_kind="argmax", audio_files=audio_files, annotation_files=annotation_files)
+            self.rgb = torch.from_numpy(rgb).to(dev)
+        else:
+            audio_files, db = loaders.load_feature_dir(audio_dir, ".npy")
+            assert len(audio_files) == len(annotation_files), "Mismatch in audio and annotation file counts."
+            super().__init__(torch.from_numpy(db).to(dev), torch.from_numpy(tabs).to(dev), _lib.GTC_PATCH_CNN, (224, 224),
+                             label_kind="argmax", audio_files=audio_files, annotation_files=annotation_files)
         self.audio_dir, self.annotation_dir = audio_dir, annotation_dir
 
     @classmethod

@@ -184,6 +184,15 @@ int gtc_labels_vit_heads(const int8_t* d_tabs, const int64_t* d_index, int64_t n
 int gtc_patches(const float* d_db, const int64_t* d_index, int64_t n, int n_bins, int n_frames,
                 int out_h, int out_w, int mode, float* d_out, gtc_stream_t stream);
 
+/* The CNN loader's PICTURE route (my_dataloader.py:10,17-21,29-33): the reference decodes a PNG rendered by new_cqt.py,
+ * resizes it to 224 x 224 with PIL (host work, kept on the host: gtc_b200.loaders.load_png_dir does exactly that once per
+ * dataset) and applies ToTensor + Normalize per item.  This kernel is the per-batch part: d_rgb [n_total, h, w, 3] uint8
+ * (PIL's HWC bytes) -> d_out [n, 3, h, w] fp32 = ((x / 255) - mean[c]) / std[c], the same three correctly rounded fp32
+ * operations torchvision performs, for the items d_index[n] selects (NULL = identity).  w must be a multiple of 4. */
+int gtc_patches_rgb8(const uint8_t* d_rgb, const int64_t* d_index, int64_t n, int h, int w,
+                     float mean_r, float mean_g, float mean_b, float std_r, float std_g, float std_b,
+                     float* d_out, gtc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Batch augmentation and dB normalisation -- replaces the torch op chains of /root/reference/ViT_engine.py:28-117
  * (time_shift :28-42, add_noise :44-47, frequency_mask :49-63, time_mask :65-79, composed by augment_batch :81-93,

@@ -192,3 +192,49 @@ def test_cnn_dataloader_contract(dataset_dirs):
     loss = out.mean() + labels[:, 0].float().mean()
     assert torch.isfinite(loss)
     assert len(md.GuitarTabDataset(str(root / "cqt"), str(root / "tab"))) == 103
+
+
+def test_cnn_loader_reads_the_reference_pictures_bit_exactly(lib, tmp_path):
+    """my_dataloader.py's own input: a directory of PNG pictures (new_cqt.py renders ~775 x 308 RGBA figures).  The drop-in
+    decodes + resizes with PIL on the host like the reference and does ToTensor + Normalize on the GPU; every item and
+    every batch must equal torchvision's transform of my_dataloader.py:17-21 bit for bit, labels = argmax (:40-44)."""
+    import torch
+    from PIL import Image
+    from torchvision import transforms
+    import my_dataloader
+    rng = np.random.default_rng(3)
+    pics, labs = tmp_path / "pics", tmp_path / "tabs"
+    pics.mkdir(); labs.mkdir()
+    n = 23
+    for i in range(n):
+        h, w = (308, 775) if i % 3 else (240, 320)
+        a = (rng.random((h, w, 4)) * 255).astype(np.uint8)
+        a[..., 3] = 255
+        a[: h // 2, :, 0] = np.linspace(0, 255, w).astype(np.uint8)           # some structure besides noise
+        Image.fromarray(a, "RGBA").save(pics / f"clip_{i:03d}.png")
+        tab = np.zeros((6, 19), np.int8)
+        for s_ in range(6):
+            if rng.random() < 0.7:
+                tab[s_, rng.integers(0, 19)] = 1
+        np.save(labs / f"clip_{i:03d}.npy", tab)
+    tf = transforms.Compose([transforms.Resize((224, 224)), transforms.ToTensor(),
+                             transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    names = sorted(os.listdir(pics))
+    want_x = torch.stack([tf(Image.open(pics / f).convert("RGB")) for f in names])
+    want_y = torch.stack([torch.tensor(np.argmax(np.load(labs / f.replace(".png", ".npy")), axis=1), dtype=torch.long) for f in names])
+    ds = my_dataloader.GuitarTabDataset(str(pics), str(labs))
+    assert len(ds) == n and ds.audio_files == names
+    x0, y0 = ds[5]
+    assert x0.dtype == torch.float32 and tuple(x0.shape) == (3, 224, 224) and torch.equal(x0.cpu(), want_x[5]) and torch.equal(y0.cpu(), want_y[5])
+    torch.manual_seed(5)
+    train, val, test = my_dataloader.create_dataloaders(str(pics), str(labs), batch_size=4)
+    seen = 0
+    for loader in (train, val, test):
+        base = loader.dataset.dataset if hasattr(loader.dataset, "dataset") else loader.dataset
+        for xb, yb in loader:
+            assert xb.is_cuda and tuple(xb.shape[1:]) == (3, 224, 224) and yb.dtype == torch.int64 and tuple(yb.shape[1:]) == (6,)
+            seen += xb.shape[0]
+        idx = torch.tensor(loader.dataset.indices)
+        xb, yb = base.batch(idx.to("cuda"))
+        assert torch.equal(xb.cpu(), want_x[idx]) and torch.equal(yb.cpu(), want_y[idx])
+    assert seen == n
