@@ -75,3 +75,55 @@ def test_outputs_and_workspace_stay_inside_their_buffers(lib, recipe):
     torch.cuda.synchronize()
     bad = [i for i, gd in enumerate(guards) if not gd.intact()]
     assert not bad, f"guard bands overwritten for buffers {bad} of {len(guards)}"
+
+
+def test_inputs_are_not_read_beyond_their_ends(lib, recipe):
+    """Read side: the inputs sit between guard bands of NaN (fp32 / fp64) or of an impossible value (int8 labels = 77).
+    A read past either end that reaches a result shows up as a NaN or as a different result -- the operator GEMM would
+    spread a single NaN sample over its whole segment."""
+    from gtc_b200 import ops, synth, _lib
+    dev = torch.device("cuda")
+    lens = np.array([SR * 2 + 37, 4000, SR + 777, 4410], dtype=np.int64)
+    a_np = np.concatenate([make_test_audio(int(n), 80 + i) for i, n in enumerate(lens)])
+
+    def nan_guarded(arr, fill=float("nan")):
+        arr = np.ascontiguousarray(arr)
+        pad = 1024
+        raw = torch.full((pad + arr.size + pad,), fill, dtype=torch.from_numpy(arr).dtype, device=dev)
+        raw[pad:pad + arr.size] = torch.from_numpy(arr.reshape(-1)).to(dev)
+        return raw[pad:pad + arr.size].view(arr.shape)
+
+    for engine in (_lib.GTC_GEMM_TCGEN05_FP16X2, _lib.GTC_GEMM_SIMT_FP32):
+        plan = ops.CqtPlan(recipe, engine=engine)
+        co, so = plan.offsets(lens)
+        n_seg = int(so[-1])
+        co_t, so_t = torch.from_numpy(co).to(dev), torch.from_numpy(so).to(dev)
+        want = plan.segments_db(torch.from_numpy(a_np).to(dev), co_t, so_t, n_seg).clone()
+        got = plan.segments_db(nan_guarded(a_np), co_t, so_t, n_seg)
+        assert bool(torch.isfinite(got).all()) and torch.equal(got, want)
+        plan.close()
+    sp = ops.StructuredCqtPlan(recipe)
+    starts = torch.tensor([0, len(a_np) - 3000], dtype=torch.int64, device=dev)          # the last segment ends at the buffer end
+    valid = torch.tensor([4410, 3000], dtype=torch.int32, device=dev)
+    seglen = torch.tensor([4410, 4410], dtype=torch.int32, device=dev)
+    s_want = sp.segments_db(torch.from_numpy(a_np).to(dev), starts, valid, seglen, 4410).clone()
+    s_got = sp.segments_db(nan_guarded(a_np), starts, valid, seglen, 4410)
+    assert bool(torch.isfinite(s_got).all()) and torch.equal(s_got, s_want)
+    sp.close()
+
+    db = want
+    idx = torch.tensor([n_seg - 1, 0, n_seg - 1], dtype=torch.int64, device=dev)
+    for mode in (_lib.GTC_PATCH_VIT, _lib.GTC_PATCH_CNN):
+        p_want = ops.patches(db, index=idx, mode=mode)
+        p_got = ops.patches(nan_guarded(db.cpu().numpy()), index=idx, mode=mode)
+        assert bool(torch.isfinite(p_got).all()) and torch.equal(p_got, p_want)
+
+    on, du, pi, eoff = synth.note_events([n / SR for n in lens], seed=3)
+    t_ = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    times = np.concatenate([(np.arange(int(so[c + 1] - so[c])) + 0.5) * 0.1 for c in range(len(lens))])
+    l_want, st_want = ops.rasterize_tabs(t_(on), t_(du), t_(pi), t_(eoff), t_(times), t_(so))
+    l_got, st_got = ops.rasterize_tabs(nan_guarded(on), nan_guarded(du), nan_guarded(pi), t_(eoff), nan_guarded(times), t_(so))
+    assert torch.equal(l_got, l_want) and torch.equal(st_got, st_want)
+    tabs_g = nan_guarded(l_want.cpu().numpy(), fill=77)
+    assert torch.equal(ops.labels_argmax(tabs_g, idx), ops.labels_argmax(l_want, idx))
+    assert all(torch.equal(a, b) for a, b in zip(ops.labels_vit_heads(tabs_g, idx), ops.labels_vit_heads(l_want, idx)))
