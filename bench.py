@@ -44,7 +44,7 @@ def workload_config(n_clips=N_CLIPS):
                         "cqt.py CQT+|.|^4+dB+cut, jam_to_tablature labels, ViT_dataloader (3,224,224) patches" % (n_clips, CLIP_SECONDS),
             "clips_per_gpu": n_clips, "segments_per_gpu": n_clips * segs, "sr": SR, "seg_len": 4410, "seg_hop": 2205,
             "n_bins": 96, "frames": 5, "patch": [3, 224, 224],
-            "cache": "per-step inputs (0.95 GB audio) and outputs (65 GB of patches through an 11 GB ring) exceed the 126 MB L2; no flush needed"}
+            "cache": "per-step inputs (0.95 GB audio) and outputs (65 GB of patches through a 17 GB ring) exceed the 126 MB L2; no flush needed"}
 
 
 # ======================================================================================================================
@@ -424,8 +424,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=N_CLIPS)
-    ap.add_argument("--chunk-segments", type=int, default=19200, help="upper limit of segments per chunk; the planner ends chunks where the GEMM tile waves are full")
-    ap.add_argument("--patch-batch", type=int, default=19200, help="segments per patch launch (one launch per chunk measured fastest)")
+    ap.add_argument("--chunk-segments", type=int, default=28400, help="upper limit of segments per chunk; the planner ends chunks where the GEMM tile waves are full")
+    ap.add_argument("--patch-batch", type=int, default=28400, help="segments per patch launch (one launch per chunk measured fastest)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ramp", action="store_true", help="e2e arm: equal chunks instead of the ramped first/last chunks")
     ap.add_argument("--host-audio", default="pcm16", choices=["pcm16", "f32"], help="sample type of the pinned host audio of the e2e arm")

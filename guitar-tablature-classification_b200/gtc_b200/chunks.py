@@ -14,10 +14,15 @@ import numpy as np
 
 GEMM_TILE_M = 128                           # cqt_gemm_tc.cu TBM
 GEMM_TILE_WIDTHS = (256, 240, 192, 128, 64)  # cqt_gemm_tc.cu kTileWidths: the first that divides n_out
-# host-input head, as fractions of the chunk limit: one, one, two, two, three, three quarters -- with the limit at four
-# GEMM waves these are chunks of 1, 1, 2, 2, 3, 3 FULL waves (the efficiency rule below trims 16/32/48 clips to 15/31/47),
-# so the small chunks of the ramp do not pay for half-empty waves.  GTC_RAMP="f0,f1,..." overrides it for experiments.
-RAMP_FRACTIONS = (0.25, 0.25, 0.5, 0.5, 0.75, 0.75)
+# host-input head in GEMM waves: chunks of 1, 1, 2, 2, 3, 3 FULL waves (15, 15, 31, 31, 47, 47 clips of 30 s on 148 SMs), so
+# the small chunks of the ramp do not pay for half-empty waves.  GTC_RAMP="w0,w1,..." overrides it for experiments.
+RAMP_WAVES = (1, 1, 2, 2, 3, 3)
+
+
+def rows_per_wave(n_out: int, sm_count: int) -> int:
+    """Operand rows one full wave of GEMM tiles covers: sm_count tiles of GEMM_TILE_M rows, ceil(n_out / width) per row block."""
+    width = next((w for w in GEMM_TILE_WIDTHS if n_out % w == 0), GEMM_TILE_WIDTHS[0])
+    return int(sm_count) * GEMM_TILE_M // -(-int(n_out) // width)
 
 
 def gemm_tiles(n_seg: int, n_clips: int, parts: int, n_out: int) -> int:
@@ -37,20 +42,22 @@ def wave_efficiency(n_seg: int, n_clips: int, parts: int, n_out: int, sm_count: 
 
 
 def plan_bounds(n_seg_per_clip: Sequence[int], limit: int, ramp: bool = False,
-                efficiency: Optional[Callable[[int, int], float]] = None) -> List[Tuple[int, int]]:
+                efficiency: Optional[Callable[[int, int], float]] = None, wave_rows: Optional[int] = None) -> List[Tuple[int, int]]:
     """[(first clip, end clip)] of every chunk: whole clips, at most ``limit`` segments (a single longer clip is its own
-    chunk).  ``ramp``: the first chunks hold RAMP_FRACTIONS of the limit -- while chunk k is computed the copy engine
-    delivers 1.1-1.5 x as many clips (PCIe ~46 GB/s of int16 PCM against ~31 clips/ms of kernels), so each chunk finds
-    its audio resident; there is no ramp-down because the last chunk's device->host copy hides under its own patch stores.
+    chunk).  ``ramp``: the first chunks hold RAMP_WAVES waves of ``wave_rows`` rows each (an eighth of the limit, growing,
+    when ``wave_rows`` is not given) -- the copy engine delivers ~37 clips/ms of int16 PCM (PCIe ~50 GB/s) against ~31
+    clips/ms of kernels, so a chunk may be at most ~1.2 x + a head start larger than its predecessor if it is to find its
+    audio resident; there is no ramp-down because the last chunk's device->host copy hides under its own patch stores.
     ``efficiency(n_seg, n_clips)``: when given, a chunk that is followed by more clips ends, within the last 20 % of its
     greedy size, where the efficiency is highest (ties: the larger chunk)."""
     nseg = np.asarray(n_seg_per_clip, dtype=np.int64)
     seg_off = np.concatenate([[0], np.cumsum(nseg)])
     n_clips, total = len(nseg), int(seg_off[-1])
-    fractions = RAMP_FRACTIONS
+    waves = RAMP_WAVES
     if os.environ.get("GTC_RAMP"):
-        fractions = tuple(float(x) for x in os.environ["GTC_RAMP"].split(","))
-    sizes = [int(limit * f) for f in fractions] if ramp and total > 3 * limit else []
+        waves = tuple(float(x) for x in os.environ["GTC_RAMP"].split(","))
+    unit = wave_rows if wave_rows else max(1, limit // 8)
+    sizes = [min(limit, int(w * unit)) for w in waves] if ramp and total > 3 * limit else []
     bounds, c0, k = [], 0, 0
     while c0 < n_clips:
         cap = sizes[k] if k < len(sizes) else limit

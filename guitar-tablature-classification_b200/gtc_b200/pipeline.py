@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .chunks import plan_bounds
+from .chunks import plan_bounds, rows_per_wave
 from .cqt_design import CqtRecipe
 
 
@@ -128,8 +128,8 @@ class _Staging:
 
 class FrontEnd:
     def __init__(self, recipe: CqtRecipe = CqtRecipe(), device: Optional[int] = None, engine: Optional[int] = None,
-                 patch_mode: int = _lib.GTC_PATCH_VIT, img_size=(224, 224), chunk_segments: int = 19200,
-                 patch_batch: int = 19200, overlap: bool = False, gemm_ctas: int = 64,
+                 patch_mode: int = _lib.GTC_PATCH_VIT, img_size=(224, 224), chunk_segments: int = 28400,
+                 patch_batch: int = 28400, overlap: bool = False, gemm_ctas: int = 64,
                  patch_ctas_per_sm: int = 4, coresident: bool = False, wave_aware: bool = True):
         """``coresident=True``: the patch kernels run on their own lower-priority stream, gated only by their chunk's dB
         features, while the GEMM stream goes on with the next chunks, so that (with libgtc built -DTC_MAXNREG=152) one
@@ -184,7 +184,8 @@ class FrontEnd:
         full = self.chunk_segments
         eff = (lambda n, c: self.plan.gemm_wave_efficiency(n, c)) if self.wave_aware else None
         chunks = []
-        for c0, c1 in plan_bounds(nseg, full, ramp=ramp, efficiency=eff):
+        wave = rows_per_wave(2 * self.plan.n_bins * self.plan.n_frames, self.plan.sm_count)
+        for c0, c1 in plan_bounds(nseg, full, ramp=ramp, efficiency=eff, wave_rows=wave):
             ch = _Chunk(c0, c1, int(clip_off[c0]), int(clip_off[c1]), int(seg_off[c0]), int(seg_off[c1]),
                         int(inp.evt_off[c0]), int(inp.evt_off[c1]))
             assert ch.g1 - ch.g0 <= max(self.chunk_segments, int(nseg[c0]))

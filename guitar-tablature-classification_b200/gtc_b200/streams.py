@@ -65,7 +65,7 @@ def stream_corpus(n_clips: int, clip_seconds: float, rank: int = 0, world_size: 
     n_samples = int(sr * clip_seconds)
     mine = shard.partition_round_robin(n_clips, rank, world_size)
     patch_mode = _lib.GTC_PATCH_VIT if mode == "vit" else _lib.GTC_PATCH_CNN
-    chunk_segments = 19200                                          # FrontEnd default: four full GEMM tile waves of 30 s clips
+    chunk_segments = 28400                                          # FrontEnd default: six full GEMM tile waves of 30 s clips
     ring = max(batch_size, (chunk_segments // batch_size) * batch_size)   # whole batches per patch launch
     fe = FrontEnd(recipe, device=dev_index, patch_mode=patch_mode, chunk_segments=chunk_segments, patch_batch=ring)
     rep = StreamReport(label_stats=np.zeros(3, dtype=np.int64))

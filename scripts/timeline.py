@@ -8,7 +8,7 @@ from gtc_b200 import CqtRecipe, synth
 from gtc_b200.pipeline import FrontEnd, ShardInputs
 ap = argparse.ArgumentParser()
 ap.add_argument("--host", action="store_true"); ap.add_argument("--steps", type=int, default=2)
-ap.add_argument("--clips", type=int, default=360); ap.add_argument("--chunk-segments", type=int, default=19200)
+ap.add_argument("--clips", type=int, default=360); ap.add_argument("--chunk-segments", type=int, default=28400)
 a = ap.parse_args()
 dev = torch.device("cuda:0"); SR = 22050; n = SR * 30
 audio = synth.pluck_clips(a.clips, n, sr=SR, seed=1, device=dev, block=24).reshape(-1)

@@ -170,7 +170,7 @@ def test_full_size_shard_spot_checks(lib, recipe, basis_cache):
     inp = ShardInputs(audio, lens, torch.from_numpy(ev).to(dev), eoff, sr=SR)
     out = fe.run(inp, device_inputs=True, consumer=consumer)
     torch.cuda.synchronize()
-    assert out.n_seg == n_seg and len(fe.plan_chunks(inp)) == 6 and len(grabbed) == 48
+    assert out.n_seg == n_seg and len(fe.plan_chunks(inp)) == 4 and len(grabbed) == 48
     assert not any(bool(c) for c in chan_diff)                      # ViT_dataloader.py:50 repeat(3, 1, 1)
     db = out.db
     assert bool(((db == -120) | ((db >= -60) & (db <= 0))).all())  # cqt_lim value set

@@ -196,10 +196,17 @@ def test_chunk_planner_properties():
     assert [c1 - c0 for c0, c1 in wave] == [63, 63, 63, 63, 63, 45]                       # 63 clips = 18 900 rows = 592 tiles
     assert ck.gemm_tiles(63 * 299, 63, parts, n_out) == 4 * sm and eff(63 * 299, 63) == 1.0
     assert abs(eff(54 * 299, 54) - 508 / 592) < 1e-12                                     # the old 54-clip chunks: 3.43 waves
-    ramp = ck.plan_bounds(nseg, 19200, ramp=True, efficiency=eff)
+    wave_rows = ck.rows_per_wave(n_out, sm)
+    assert wave_rows == 148 * 128 // 4
+    ramp = ck.plan_bounds(nseg, 19200, ramp=True, efficiency=eff, wave_rows=wave_rows)
     sizes = [c1 - c0 for c0, c1 in ramp]
     assert sizes[:7] == [15, 15, 31, 31, 47, 47, 63] and sum(sizes) == 360 and max(sizes) <= 64   # 1,1,2,2,3,3,4 full waves
     assert all(eff(299 * n, n) > 0.95 for n in sizes[:7])
+    # the default limit is six waves: 94 clips per chunk, the same ramp in front
+    six = ck.plan_bounds(nseg, 28400, efficiency=eff)
+    assert [c1 - c0 for c0, c1 in six] == [94, 94, 94, 78] and eff(94 * 299, 94) > 0.99
+    six_ramp = [c1 - c0 for c0, c1 in ck.plan_bounds(nseg, 28400, ramp=True, efficiency=eff, wave_rows=wave_rows)]
+    assert six_ramp[:6] == [15, 15, 31, 31, 47, 47] and sum(six_ramp) == 360
     # ragged shard: zero-segment clips, one clip longer than the limit, random lengths
     rng = np.random.default_rng(5)
     nseg = rng.integers(0, 400, size=97)
