@@ -38,6 +38,9 @@ class ShardInputs:
 
 @dataclass
 class ShardOutputs:
+    """Results of one ``FrontEnd.run``.  ``db`` / ``tabs`` are views into buffers the FrontEnd owns and REUSES: they are valid
+    (in stream order on the caller's current stream; after a synchronize for the pinned host copies) until the next ``run``
+    of the same FrontEnd -- copy what must outlive it.  Patch batches are only ever handed to ``consumer``."""
     db: Optional[torch.Tensor] = None          # [n_seg, n_bins, T] fp32 (host pinned for e2e, device otherwise)
     tabs: Optional[torch.Tensor] = None        # [n_seg, 6, 19] int8
     stats: Optional[np.ndarray] = None         # total, with_notes, with_first_string
