@@ -134,7 +134,8 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
                              "sample": f"{workers} clips x {clip_s:.0f} s per step on {workers} processes "
                                        "(restated NumPy/SciPy oracle of cqt.py + jam_to_tablature.py + ViT_dataloader.py, "
-                                       ".npy I/O on tmpfs; librosa/soxr/jams are not installable, so this is a port, not librosa)"},
+                                       ".npy I/O on tmpfs; librosa/soxr/jams are not installable, so this is a port, not librosa; "
+                                       "time = rounds x the slowest worker's busy time, process start-up and imports excluded)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -202,6 +203,104 @@ def physical_gpu_index(local_rank: int) -> int:
     return local_rank
 
 
+def hostlink_floor(fe, inp_host, chunk_plan, out, world, dev, iters=5, d2h=True):
+    """Copies only: the end-to-end arm's bytes per step (int16 PCM + events up in `stage_piece_clips`-clip pieces, dB
+    features + labels down once per chunk) with no kernel in between, every rank at the same time.  The fastest step the
+    box's host links allow -> `e2e.hostlink_frac` = this floor / the measured e2e step (scripts/hostlink_bench.py sweeps
+    the granularities; profiles/r02_hostlink.md)."""
+    import torch
+    import torch.distributed as dist
+    n_in = inp_host.audio.numel()
+    d_in = torch.empty(n_in, dtype=inp_host.audio.dtype, device=dev)
+    d_ev = torch.empty(inp_host.events.shape, dtype=torch.float64, device=dev)
+    n_seg = out.n_seg
+    d_db = torch.zeros((n_seg, 96, 5), dtype=torch.float32, device=dev) if d2h else None
+    d_tab = torch.zeros((n_seg, 6, 19), dtype=torch.int8, device=dev) if d2h else None
+    h_db = fe._buf("db_host", (n_seg, 96, 5), torch.float32, pinned=True) if d2h else None
+    h_tab = fe._buf("tabs_host", (n_seg, 6, 19), torch.int8, pinned=True) if d2h else None
+    s_up, s_dn = fe.s_stage, fe.s_out
+    piece = fe.stage_piece_clips
+    clip_off = np.concatenate([[0], np.cumsum(inp_host.clip_lens)]).astype(np.int64)
+
+    def one():
+        with torch.cuda.stream(s_up):
+            for c in range(0, len(inp_host.clip_lens), piece):
+                a, b = int(clip_off[c]), int(clip_off[min(len(inp_host.clip_lens), c + piece)])
+                d_in[a:b].copy_(inp_host.audio[a:b], non_blocking=True)
+                if c == 0:
+                    d_ev.copy_(inp_host.events, non_blocking=True)
+        if d2h:
+            with torch.cuda.stream(s_dn):
+                for ch in chunk_plan:
+                    h_db[ch.g0:ch.g1].copy_(d_db[ch.g0:ch.g1], non_blocking=True)
+                    h_tab[ch.g0:ch.g1].copy_(d_tab[ch.g0:ch.g1], non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        one()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    s_up.wait_event(e0); s_dn.wait_event(e0)
+    for _ in range(iters):
+        one()
+    torch.cuda.current_stream().wait_stream(s_up)
+    torch.cuda.current_stream().wait_stream(s_dn)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    nbytes = n_in * inp_host.audio.element_size() + inp_host.events.numel() * 8 + (n_seg * (1920 + 114) if d2h else 0)
+    return {"ms_per_step_floor": float(ms.item()), "bytes_per_rank": int(nbytes),
+            "aggregate_GBs": world * nbytes / (float(ms.item()) * 1e-3) / 1e9}
+
+
+def ragged_corpus(n_clips_total, seed=1):
+    """clip durations uniform in [14.6, 30.0] s (the committed label fixtures show 73..125 segments
+    of 0.2 s per clip), numpy default_rng(seed)."""
+    rng = np.random.default_rng(seed)
+    return (rng.uniform(14.6, 30.0, n_clips_total) * SR).astype(np.int64)
+
+
+def ragged_arm(args, fe, timed, rank, world, dev):
+    """Device-resident arm on ragged clips.  A corpus of 360 x world clips is dealt to the ranks (a) `c % W` as north_star
+    words it (shard.partition_round_robin) and (b) longest-first greedy by duration (shard.partition_balanced); value =
+    all ranks' seconds of audio / the slowest rank's time."""
+    import torch
+    import torch.distributed as dist
+    from gtc_b200 import synth, shard
+    from gtc_b200.pipeline import ShardInputs
+    lens_all = ragged_corpus(args.clips * world)
+    res = {"durations": "uniform [14.6, 30.0] s, numpy default_rng(1), %d clips over %d rank(s)" % (len(lens_all), world)}
+    n_max = int(SR * CLIP_SECONDS)
+    parts = [("round_robin", shard.partition_round_robin(len(lens_all), rank, world))]
+    if world > 1:
+        parts.append(("balanced", shard.partition_balanced((lens_all / SR).tolist(), rank, world)))
+    for name, ids in parts:
+        lens = lens_all[ids]
+        full = synth.pluck_clips(len(ids), n_max, sr=SR, seed=101 + rank, device=dev, block=24)
+        audio = torch.cat([full[i, : int(lens[i])] for i in range(len(ids))]).contiguous()
+        del full
+        on, du, pi, evt_off = synth.note_events((lens / SR).tolist(), seed=202 + rank)
+        events = torch.from_numpy(np.stack([on, du, pi])).to(dev)
+        inp = ShardInputs(audio, lens, events, evt_off, sr=SR)
+        plan = fe.plan_chunks(inp)
+        ms, out = timed(inp, True, args.steps, args.warmup, plans=(plan, plan, plan), events=False)
+        secs = torch.tensor([float(lens.sum()) / SR], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(secs, op=dist.ReduceOp.SUM)
+        res[name] = {"value": float(secs.item()) * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps,
+                     "segments_this_rank": int(out.n_seg), "chunks": [int(c.g1 - c.g0) for c in plan]}
+        del audio, events, inp
+    return res
+
+
+
 def run_cuda_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,7 +315,8 @@ def run_cuda_arm(args):
         cpu_baseline = {"value": a / w, "unit": UNIT, "cores": workers, "kind": "port",
                         "sample": f"{workers} clips x 10 s, one process per core ({cores} host cores), restated reference "
                                   "(cqt.py + jam_to_tablature.py + ViT_dataloader.py loops on the NumPy/SciPy oracle, .npy I/O on tmpfs); "
-                                  "not librosa -- it is not installable here"}
+                                  "not librosa -- it is not installable here; time = the slowest worker's busy time, process start-up "
+                                  "and imports excluded"}
 
     import torch
     import torch.distributed as dist
@@ -280,15 +380,16 @@ def run_cuda_arm(args):
     # PAGEABLE host memory, which synchronises the stream first -- one hidden host sync per step.)
     stats_head = torch.tensor([n_clips, 0, int(lens.sum())], dtype=torch.int64).pin_memory()
 
-    def step(inp, device_inputs, last=False, first=False):
+    def step(inp, device_inputs, last=False, first=False, host_outputs=True, plans=None):
         # host-input arm: the next step's shard (the same pinned buffers stand in for it) is prefetched behind this
         # step's copies, as a training loop would do with the next shard of the corpus; the last step prefetches nothing
         # a cold step ramps its chunks up from 15 clips (its audio is still on the bus); a prefetched step finds ~90 clips
         # resident and uses the same full-wave chunks as the device-resident arm
         pref = args.prefetch and not device_inputs
-        mine = chunks if device_inputs else (chunks_flat_host if (pref and not first and args.flat_after_first) else chunks_host)
-        nxt = chunks_flat_host if args.flat_after_first else chunks_host
-        out = fe.run(inp, device_inputs=device_inputs, chunks=mine,
+        p_dev, p_ramp, p_flat = plans if plans is not None else (chunks, chunks_host, chunks_flat_host)
+        mine = p_dev if device_inputs else (p_flat if (pref and not first and args.flat_after_first) else p_ramp)
+        nxt = p_flat if args.flat_after_first else p_ramp
+        out = fe.run(inp, device_inputs=device_inputs, chunks=mine, want_host_outputs=host_outputs,
                      next_inp=inp if (pref and not last) else None, next_chunks=nxt)
         # tiny per-shard stats gather (the path's only collective), jam_to_tablature.py:376-378
         stats_head[1] = out.n_seg
@@ -303,22 +404,22 @@ def run_cuda_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(inp, device_inputs, steps, warmup):
+    def timed(inp, device_inputs, steps, warmup, host_outputs=True, plans=None, events=True):
         for _ in range(warmup):
-            step(inp, device_inputs, last=True, first=True)   # warm-up steps prefetch nothing: the timed region starts cold
+            step(inp, device_inputs, last=True, first=True, host_outputs=host_outputs, plans=plans)   # warm-up steps prefetch nothing: the timed region starts cold
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        fe.patch_events = [] if device_inputs else None      # per-launch CUDA events on the launching stream, timed region only
-        fe.gemm_events = [] if device_inputs else None
+        fe.patch_events = [] if (device_inputs and events) else None      # per-launch CUDA events on the launching stream, timed region only
+        fe.gemm_events = [] if (device_inputs and events) else None
         e0.record()
         out = None
         t_host = time.perf_counter()
         for i in range(steps):
-            out = step(inp, device_inputs, last=(i == steps - 1), first=(i == 0))
+            out = step(inp, device_inputs, last=(i == steps - 1), first=(i == 0), host_outputs=host_outputs, plans=plans)
         timed.host_ms = 1e3 * (time.perf_counter() - t_host) / max(1, steps)     # CPU time to enqueue one step
         e1.record()
         barrier()
-        if device_inputs:
+        if device_inputs and events:
             timed.patch_launches = [(a.elapsed_time(b), n) for a, b, n in fe.patch_events]
             timed.gemm_launches = [(a.elapsed_time(b), n) for a, b, n in fe.gemm_events]
         fe.patch_events = fe.gemm_events = None
@@ -331,6 +432,15 @@ def run_cuda_arm(args):
         ms_dev, out_dev = timed(inp_dev, True, args.steps, args.warmup)
     host_ms_dev = timed.host_ms
     ms_e2e, out_e2e = timed(inp_host, False, args.steps, args.warmup)
+    # training flow (BASELINE configs[3]/[4]): the engines consume features, labels and patches ON the device
+    # (bestengine.py:899-901, ViT_engine.py:277-278), so only the label stats return to the host
+    ms_train, out_train = timed(inp_host, False, args.steps, args.warmup, host_outputs=False)
+    # what the box's host links can move: the same bytes per step, same copy granularity, no kernels, all ranks at once
+    link = hostlink_floor(fe, inp_host, chunks_flat_host, out_e2e, world, dev, iters=max(3, min(args.steps, 10)))
+    link_train = hostlink_floor(fe, inp_host, chunks_flat_host, out_train, world, dev, iters=max(3, min(args.steps, 10)), d2h=False)
+    ragged = None
+    if not args.no_ragged:
+        ragged = ragged_arm(args, fe, timed, rank, world, dev)
 
     # dominant kernel (patch store stream) timed live, per launch, on its own stream
     n_seg = out_dev.n_seg
@@ -392,7 +502,17 @@ def run_cuda_arm(args):
                         "host_audio": "int16 PCM (the WAV files' samples; x/32768 on the device == librosa.load)" if args.host_audio == "pcm16" else "fp32",
                         "note": "pinned host audio+events in, dB features + labels + stats back; patches stay in HBM for the engines",
                         "prefetch": bool(args.prefetch),
-                        "cpu_affinity": numa},
+                        "cpu_affinity": numa,
+                        "hostlink": link,
+                        "hostlink_frac": link["ms_per_step_floor"] / (ms_e2e / args.steps),
+                        "hostlink_note": "hostlink = the same bytes per step moved with NO kernels (same copy granularity, all ranks at once, device "
+                                         "events, max over ranks): the floor the box's host links set for this arm; frac = floor / measured step"},
+                "e2e_train": {"value": world * seconds_per_step * args.steps / (ms_train * 1e-3), "unit": UNIT, "ms_per_step": ms_train / args.steps,
+                              "h2d_bytes_per_step": out_train.h2d_bytes, "d2h_bytes_per_step": out_train.d2h_bytes,
+                              "note": "training flow of BASELINE configs[3]/[4]: pinned host audio+events in; features, labels and patches stay in HBM "
+                                      "for the engines (bestengine.py:899-901), only the label stats return",
+                              "hostlink": link_train, "hostlink_frac": link_train["ms_per_step_floor"] / (ms_train / args.steps)},
+                "ragged": ragged,
                 "gpu_launches": out_dev.launches * args.steps, "host_enqueue_ms_per_step": host_ms_dev,
                 "roofline": {"bound": "hbm", "kernel": "patch_kernel<5> (gtc_patches)", "achieved": achieved, "peak": peak_hbm,
                              "unit": "GB/s", "frac": achieved / peak_hbm, "traffic": traffic,
@@ -427,6 +547,7 @@ def main():
     ap.add_argument("--chunk-segments", type=int, default=28400, help="upper limit of segments per chunk; the planner ends chunks where the GEMM tile waves are full")
     ap.add_argument("--patch-batch", type=int, default=28400, help="segments per patch launch (one launch per chunk measured fastest)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ragged", action="store_true", help="skip the ragged-duration arm (SURVEY 8d config 2 durations)")
     ap.add_argument("--no-ramp", action="store_true", help="e2e arm: equal chunks instead of the ramped first/last chunks")
     ap.add_argument("--host-audio", default="pcm16", choices=["pcm16", "f32"], help="sample type of the pinned host audio of the e2e arm")
     ap.add_argument("--engine", type=int, default=None, help="GEMM engine: 0 tcgen05 3xTF32, 1 SIMT fp32, 2 tcgen05 fp16x2 (default: library default)")

@@ -470,7 +470,7 @@ class FrontEnd:
             # ---- stats (tiny) and join
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_stream(self.s_comp)
-                if host_out:
+                if not device_inputs:                               # host-input runs always return the label stats
                     h_stats = self._buf("stats_host", (3,), torch.int64, pinned=True)
                     h_stats.copy_(stats, non_blocking=True)
                     out.d2h_bytes += 24
@@ -487,7 +487,7 @@ class FrontEnd:
                 self._stage_free[stage.slot].record(torch.cuda.current_stream())
             if next_inp is not None and not device_inputs:
                 self.prefetch(next_inp, next_chunks)
-        self._last_stats = (stats, self._bufs.get(("stats_host", True)) if host_out else None)
+        self._last_stats = (stats, self._bufs.get(("stats_host", True)) if not device_inputs else None)
         return out
 
     def stats(self) -> np.ndarray:

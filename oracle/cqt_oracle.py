@@ -56,8 +56,10 @@ def lsx_kaiser_beta(att: float, tr_bw: float) -> float:
     return 0.
 
 
-def soxr_hq_halfband_taps() -> np.ndarray:
+def soxr_hq_halfband_taps(beta_scale: float = 1.0, taps_delta: int = 0, fc_scale: float = 1.0, rho: float = .5) -> np.ndarray:
     """Taps of the single 2:1 DFT stage libsoxr builds for quality SOXR_HQ, io_ratio 2, linear phase.
+    The keyword arguments perturb the design (Kaiser beta x beta_scale, tap count + taps_delta, cut-off x fc_scale, the
+    `rho` of the window argument) for scripts/tap_sensitivity.py; the defaults are libsoxr's values.
 
     soxr.c:soxr_quality_spec -> precision 20 bits, passband_end = 1 - .05/TO_3dB(rej), stopband_begin = 1;
     cr.c:_soxr_init        -> one pre-stage L=1, M=2, att = (20+1)*6.0206 dB, dft_stage_init(Fp, Fs, Fn=2, k=-4)
@@ -78,13 +80,16 @@ def soxr_hq_halfband_taps() -> np.ndarray:
     n = int(math.ceil(a / tr_bw + 1))
     modulo = 4                                   # k = -4  ->  num_taps == 1 (mod 4)
     n = (n + modulo - 2) // modulo * modulo + 1
+    n += int(taps_delta)
+    beta *= beta_scale
+    Fc *= fc_scale
     m = n - 1
     i = np.arange(n, dtype=np.float64)
     z = i - .5 * m
     x = z * math.pi
     with np.errstate(invalid="ignore", divide="ignore"):
         h = np.where(x != 0, np.sin(Fc * x) / x, Fc)
-    y = z * (1 / (.5 * m + .5))
+    y = z * (1 / (.5 * m + rho))
     h = h * np.i0(beta * np.sqrt(np.maximum(0.0, 1 - y * y))) / np.i0(beta)
     half = m // 2
     h[m - np.arange(half + 1)] = h[: half + 1]   # lsx_make_lpf computes i <= m/2 and mirrors h[m-i] = h[i]
@@ -99,6 +104,24 @@ def halfband_taps() -> np.ndarray:
     if _TAPS is None:
         _TAPS = soxr_hq_halfband_taps()
     return _TAPS
+
+
+class taps_override:
+    """``with taps_override(h): ...`` -- evaluate the oracle with another 2:1 decimator (odd length, centre tap in the
+    middle): scripts/tap_sensitivity.py (perturbed designs) and scripts/pin_with_librosa.py (taps measured from soxr)."""
+
+    def __init__(self, h):
+        self.h = np.asarray(h, dtype=np.float64)
+        assert self.h.ndim == 1 and len(self.h) % 2 == 1
+
+    def __enter__(self):
+        global _TAPS
+        self.prev, _TAPS = _TAPS, self.h
+        return self
+
+    def __exit__(self, *a):
+        global _TAPS
+        _TAPS = self.prev
 
 
 def resample_2to1(y: np.ndarray) -> np.ndarray:
