@@ -285,6 +285,16 @@ _MEM_CACHE: dict = {}
 def get_operator(recipe: CqtRecipe, seg_len: int | None = None) -> np.ndarray:
     """build_operator with an in-process and an on-disk cache (the design takes a few seconds)."""
     seg_len = recipe.seg_len if seg_len is None else int(seg_len)
+    measured = os.environ.get("GTC_OPERATOR_FILE")
+    if measured:
+        # an operator measured from the real librosa.cqt (scripts/pin_with_librosa.py --operator-out); used only where
+        # its shape fits the recipe, so inference / new_cqt plans of other geometries keep the designed operator
+        key = ("file", measured, seg_len, recipe.n_bins)
+        if key not in _MEM_CACHE:
+            op = np.load(measured)
+            _MEM_CACHE[key] = op if op.shape == (2 * recipe.n_bins * n_frames_of(recipe, seg_len), seg_len) else None
+        if _MEM_CACHE[key] is not None:
+            return _MEM_CACHE[key]
     design = {k: v for k, v in asdict(recipe).items() if k in
               ("sr", "hop_length", "n_bins", "bins_per_octave", "filter_scale", "sparsity")}
     design.update(fmin=recipe.fmin_hz, seg_len=seg_len, v=3)

@@ -41,7 +41,10 @@ class CqtPlan:
     """Device-resident segment operator for one recipe (replaces the per-call basis rebuild of librosa.cqt)."""
 
     def __init__(self, recipe: CqtRecipe = CqtRecipe(), device: Optional[int] = None, engine: Optional[int] = None,
-                 seg_len: Optional[int] = None, seg_hop: Optional[int] = None):
+                 seg_len: Optional[int] = None, seg_hop: Optional[int] = None, operator: Optional[np.ndarray] = None):
+        """``operator``: a (2 * n_bins * T, seg_len) float32 matrix to evaluate instead of the designed one, row =
+        (t * n_bins + bin) * 2 + {re, im} -- e.g. measured from the real ``librosa.cqt`` by scripts/pin_with_librosa.py
+        (exact soxr behaviour without restating it).  ``GTC_OPERATOR_FILE`` does the same for every plan of that shape."""
         lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.GtcError("CqtPlan needs a CUDA device (there is no CPU fallback)")
@@ -52,8 +55,9 @@ class CqtPlan:
         self.n_bins = recipe.n_bins
         self.n_frames = n_frames_of(recipe, self.seg_len)
         self.engine = _lib.GTC_GEMM_TCGEN05_FP16X2 if engine is None else int(engine)
-        op = np.ascontiguousarray(get_operator(recipe, self.seg_len), dtype=np.float32)
-        assert op.shape == (2 * self.n_bins * self.n_frames, self.seg_len)
+        op = np.ascontiguousarray(get_operator(recipe, self.seg_len) if operator is None else operator, dtype=np.float32)
+        if op.shape != (2 * self.n_bins * self.n_frames, self.seg_len):
+            raise _lib.GtcError(f"operator of shape {op.shape}, expected {(2 * self.n_bins * self.n_frames, self.seg_len)}")
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(lib.gtc_cqt_plan_create(C.byref(handle), self.device, self.seg_len, self.seg_hop, self.n_bins,
