@@ -1,11 +1,13 @@
-// Framing (audio -> row matrix, tf32 hi/lo split) and the dB epilogue finish of the segment CQT.
+// Framing (audio -> operand row matrix, hi/lo split) and the dB finish of the segment CQT.
 //
 // Framing: a segment of seg_len samples with hop seg_hop = seg_len / P is P consecutive "audio rows" of seg_hop
 // samples, so the GEMM's M operand is the NON-overlapping row matrix and every audio sample is read once
 // (/root/reference/cqt.py:26-45 re-slices each sample into two windows).  Clip c owns rows
 // [seg_off[c] + c*(P-1), seg_off[c+1] + (c+1)*(P-1)); row r of the clip starts at sample clip_off[c] + r*seg_hop.
-// Rows are padded to kp floats (multiple of 32 = one 128-byte TMA/UMMA swizzle atom) and written twice:
-//   hi = x rounded to tf32 (RN, low 13 mantissa bits zero), lo = x - hi (exact in fp32)      -> 3xTF32 operands.
+// Rows are padded to kp elements (a whole number of TC_KB_BYTES k-blocks = TMA/UMMA swizzle rows) and written twice:
+//   fp16x2 engine (default): hi = fp16(x * 2^8), lo = fp16(x * 2^8 - hi)          -> 22 mantissa bits in two fp16 operands
+//   3xTF32 engine          : hi = x rounded to tf32 (RN), lo = x - hi (exact fp32) -> 3xTF32 operands
+// Input samples are fp32 (librosa.load's array) or the WAV file's int16 PCM (x / 32768, exact).
 //
 // Finish: per segment, mag2 = |C|^2 of all n_bins*T outputs plus the row maximum -> |C|^power ->
 // librosa.amplitude_to_db(ref=np.amax, amin, top_db) -> cqt_lim (cqt.py:56-58), written as [n_seg, n_bins, T].

@@ -1,16 +1,24 @@
-// Tensor-core engine for the segment-operator contraction (GTC_GEMM_TCGEN05_3XTF32), sm_100a only.
+// Tensor-core engines for the segment-operator contraction, sm_100a only:
+//   GTC_GEMM_TCGEN05_FP16X2 (default)  operands split into fp16 hi + fp16 lo, tcgen05.mma.kind::f16, K = 16 per MMA
+//   GTC_GEMM_TCGEN05_3XTF32            operands split into tf32 hi + fp32 lo, tcgen05.mma.kind::tf32, K = 8 per MMA
 //
 //     C[row][n] = sum_p sum_k X[row + p][k] * Op[n][p*kp + k]          (row = audio row, n = operator row)
 //
-// 3xTF32: X = Xhi + Xlo, Op = Ohi + Olo with *hi exactly representable in tf32, and
+// Split product: X = Xhi + Xlo, Op = Ohi + Olo and
 //     C ~= Xhi*Ohi + Xlo*Ohi + Xhi*Olo        (the dropped Xlo*Olo term is ~2^-22 relative)
-// accumulated in fp32 in TMEM.  Per CTA tile: 128 rows x NC operator rows (NC <= 256, one tcgen05.mma N).
+// accumulated in fp32 in TMEM.  Per CTA tile: TBM = 128 rows x NC operator rows (NC <= 256 = one tcgen05.mma N; 240 for
+// the 960-row operator of the cqt.py recipe).
 //
-// Warp roles (192 threads, persistent CTAs, one per SM):
-//   warp 0      TMA producer : cp.async.bulk.tensor 2D tiles (128B swizzle) of Xhi/Xlo/Ohi/Olo into a smem ring
-//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=NC, K=8), commits to mbarriers;
-//                              also owns the TMEM allocation (512 columns = 2 accumulator stages)
-//   warps 2..5  epilogue     : tcgen05.ld 32x32b (thread = one row), re^2+im^2, row max, direct global stores
+// Warp roles (TC_THREADS = 64 + 32 * TC_EPI_WARPS = 320 threads, persistent CTAs, one per SM):
+//   warp 0      TMA producer : cp.async.bulk.tensor.2d tiles of Xhi/Xlo/Ohi/Olo into a TC_STAGES-deep smem ring; a stage
+//                              holds one k-block = TC_KB_BYTES bytes of K per row (default 64 B = one 64-byte swizzle row,
+//                              4 stages; gtc_common.cuh)
+//   warp 1      MMA issuer   : one elected lane issues the three split MMAs per k-step (TKB_BYTES / 32 k-steps per
+//                              k-block) and commits to mbarriers; also owns the TMEM allocation (512 columns = 2
+//                              accumulator stages of up to 256 columns)
+//   warps 2..9  epilogue     : tcgen05.ld 32x32b (thread = one row, warp = one TMEM lane quarter x one column half), K-split
+//                              partial sums added in fp32 RN registers, then re^2+im^2 + row max (or the raw complex
+//                              values) stored straight to global memory
 // The second audio row of a segment (hop = window/2, cqt.py:26-27) is just the TMA row coordinate + p.
 #include <cuda.h>
 #include "gtc_common.cuh"
@@ -24,9 +32,9 @@ constexpr int TBK = TKB_BYTES / 4;   // fp32 per k-block
 constexpr int TMAXN = 256;           // max operator rows per tile (UMMA N)
 constexpr int TSTAGES = TC_STAGES;
 constexpr int TUMMA_K = 8;           // tf32 per MMA = 32 bytes of K (16 fp16)
-constexpr uint32_t X_TILE_BYTES = TBM * TBK * 4;        // 16 KB
-constexpr uint32_t OP_TILE_BYTES = TMAXN * TBK * 4;     // 32 KB (NC rows used)
-constexpr uint32_t STAGE_BYTES = 2 * X_TILE_BYTES + 2 * OP_TILE_BYTES;   // 96 KB
+constexpr uint32_t X_TILE_BYTES = TBM * TBK * 4;        // 128 rows x TKB_BYTES   ( 8 KB at 64 B)
+constexpr uint32_t OP_TILE_BYTES = TMAXN * TBK * 4;     // 256 rows x TKB_BYTES   (16 KB at 64 B; NC rows used)
+constexpr uint32_t STAGE_BYTES = 2 * X_TILE_BYTES + 2 * OP_TILE_BYTES;   // hi + lo of both operands (48 KB at 64 B)
 constexpr uint32_t TC_SMEM_BYTES = TSTAGES * STAGE_BYTES + 1024 /*align slack*/;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
@@ -114,9 +122,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major operand tile, 128- or 64-byte swizzle: rows of TKB_BYTES, 8-row groups 8 * TKB_BYTES apart
+// K-major operand tile whose rows are ONE swizzle row of TKB_BYTES (128, 64 or 32) bytes; 8-row groups 8 * TKB_BYTES apart
 // (cute::UMMA::SmemDescriptor; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_swizzle_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);          // start address  [0,14)
   d |= (uint64_t)1 << 16;                               // leading byte offset (ignored for swizzled K-major) [16,30)
@@ -163,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   __shared__ uint32_t s_tmem_slot;
   __shared__ int s_block_done;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  // stage s : [Xhi 16K][Xlo 16K][Ohi 32K][Olo 32K]
+  // stage s : [Xhi][Xlo][Ohi][Olo]   (X_TILE_BYTES, X_TILE_BYTES, OP_TILE_BYTES, OP_TILE_BYTES)
   auto st_xhi = [&](int s) { return smem_base + s * STAGE_BYTES; };
   auto st_xlo = [&](int s) { return smem_base + s * STAGE_BYTES + X_TILE_BYTES; };
   auto st_ohi = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * X_TILE_BYTES; };
@@ -243,8 +251,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           for (int first = 1; kb < kb_end; ++kb, first = 0) {
             mbar_wait(bar_full(stage), phase);
             tc_fence_after();
-            const uint64_t dxh = make_sw128_desc(st_xhi(stage)), dxl = make_sw128_desc(st_xlo(stage));
-            const uint64_t doh = make_sw128_desc(st_ohi(stage)), dol = make_sw128_desc(st_olo(stage));
+            const uint64_t dxh = make_swizzle_desc(st_xhi(stage)), dxl = make_swizzle_desc(st_xlo(stage));
+            const uint64_t doh = make_swizzle_desc(st_ohi(stage)), dol = make_swizzle_desc(st_olo(stage));
 #pragma unroll
             for (int k = 0; k < TBK / TUMMA_K; ++k) {
               const uint64_t adv = (uint64_t)((k * TUMMA_K * 4) >> 4);   // +32 B per k-step inside the swizzle row
@@ -408,7 +416,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2D fp32 row-major [rows][cols] tensor, box = 32 floats x box_rows, 128-byte swizzle, OOB -> zeros
+// 2D row-major [rows][cols] tensor of fp32 or fp16, box = one TKB_BYTES swizzle row of K x box_rows, OOB -> zeros
 static int encode_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int elem_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return GTC_E_CUDA;

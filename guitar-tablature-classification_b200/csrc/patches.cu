@@ -13,6 +13,7 @@
 //     interpolation coefficients in registers, so a row costs 2 LDS.128 + 4T FFMA and three 16-byte streaming
 //     stores (one per channel); a warp writes 512 contiguous bytes per store instruction.
 #include <stdlib.h>
+#include <mutex>
 #include "gtc_common.cuh"
 
 namespace gtc {
@@ -257,9 +258,20 @@ rgb8_normalize_kernel(const uint8_t* __restrict__ rgb, const int64_t* __restrict
   }
 }
 
-// tickets: a small ring of counters owned by the library; each launch zeroes and uses the next slot on its stream
+// tickets: a ring of counters owned by the library, one ring per device.  A launch takes the next slot, zeroes it on its
+// stream and leaves an event behind; the launch that reuses the slot kTicketSlots launches later first makes its stream
+// wait for that event, so a counter is never reset under a kernel that is still drawing from it -- whatever streams the
+// two launches are on (a training DeviceLoader beside FrontEnd's 9 ms patch launches).
 constexpr int kTicketSlots = 1024;
 __device__ unsigned int g_patch_tickets[kTicketSlots];
+
+struct TicketRing {
+  std::mutex mu;
+  unsigned int* base = nullptr;
+  unsigned int next = 0;
+  cudaEvent_t done[kTicketSlots] = {};
+};
+static TicketRing g_ticket_rings[64];
 
 }  // namespace gtc
 
@@ -282,8 +294,11 @@ extern "C" int gtc_patches(const float* d_db, const int64_t* d_index, int64_t n,
   cudaStream_t st = (cudaStream_t)stream;
 
   const int quads = out_w / 4;
+  // the fast path stores float4: a sliced / offset output that is not 16-byte aligned takes the scalar path
   const bool fast = (out_w % 4 == 0) && quads <= kPatchThreads && (n_frames == 5 || n_frames == 9) &&
-                    n_bins * n_frames <= 96 * 16;
+                    n_bins * n_frames <= 96 * 16 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0;
+  GTC_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_db) & 3) == 0, GTC_E_ARG,
+              "gtc_patches: d_db and d_out must be 4-byte aligned");
   int threads = kPatchThreads;
   if (fast) threads = (kPatchThreads / quads) * quads;
   // row blocks: ~56 rows each (14 store iterations per thread), at least 1
@@ -291,13 +306,16 @@ extern "C" int gtc_patches(const float* d_db, const int64_t* d_index, int64_t n,
   const int rpp = (out_h + parts - 1) / parts;
   parts = (out_h + rpp - 1) / rpp;
 
-  static unsigned int* ticket_base[64] = {nullptr};   // per device: the symbol lives in every device's module image
-  static unsigned int next_slot = 0;
   int dev = 0;
   GTC_CUDA_CHECK(cudaGetDevice(&dev));
   GTC_REQUIRE(dev >= 0 && dev < 64, GTC_E_UNSUP, "gtc_patches: device ordinal %d out of range", dev);
-  if (!ticket_base[dev]) GTC_CUDA_CHECK(cudaGetSymbolAddress((void**)&ticket_base[dev], g_patch_tickets));
-  unsigned int* ticket = ticket_base[dev] + (__atomic_fetch_add(&next_slot, 1u, __ATOMIC_RELAXED) % kTicketSlots);
+  TicketRing& ring = g_ticket_rings[dev];
+  std::lock_guard<std::mutex> ring_lock(ring.mu);      // held until the launch and its event are enqueued
+  if (!ring.base) GTC_CUDA_CHECK(cudaGetSymbolAddress((void**)&ring.base, g_patch_tickets));
+  const unsigned int slot = ring.next++ % kTicketSlots;
+  if (ring.done[slot]) GTC_CUDA_CHECK(cudaStreamWaitEvent(st, ring.done[slot], 0));      // the slot's previous kernel has finished
+  else GTC_CUDA_CHECK(cudaEventCreateWithFlags(&ring.done[slot], cudaEventDisableTiming));
+  unsigned int* ticket = ring.base + slot;
   GTC_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
 
   PatchParams p{d_db, d_index, n, n_bins, n_frames, out_h, out_w, mode, prenorm, parts, rpp, ticket, d_out};
@@ -331,6 +349,7 @@ extern "C" int gtc_patches(const float* d_db, const int64_t* d_index, int64_t n,
     if (patch_max_ctas() > 0 && grid > patch_max_ctas()) grid = patch_max_ctas();
     kern<<<(unsigned)grid, threads, sm_bytes, st>>>(p);
     GTC_CUDA_CHECK(cudaGetLastError());
+    GTC_CUDA_CHECK(cudaEventRecord(ring.done[slot], st));
     return GTC_OK;
   };
   if (fast && n_frames == 5) return launch(patch_kernel<5>);

@@ -22,8 +22,15 @@ TIME_SHIFT, NOISE, FREQ_MASK, TIME_MASK = (_lib.GTC_AUG_TIME_SHIFT, _lib.GTC_AUG
                                            _lib.GTC_AUG_TIME_MASK)
 
 
-def _noise_seed() -> int:
-    return int(torch.randint(0, 2 ** 62, (1,)).item())
+def _noise_seed(like: torch.Tensor) -> int:
+    """Philox seed of the noise op, taken from the CUDA default generator of ``like``'s device: the reference's add_noise
+    calls ``torch.randn_like`` on the device tensor (ViT_engine.py:46), i.e. it consumes the CUDA generator and leaves the CPU
+    generator -- which orders the DataLoader's shuffles (loaders.sampler_order) -- alone.  No host synchronisation: the
+    generator's (seed, offset) pair is read and the offset advanced by what randn_like would consume."""
+    g = torch.cuda.default_generators[like.device.index]
+    off = int(g.get_offset())
+    g.set_offset(off + 4 * ((like.numel() + 3) // 4))
+    return (int(g.initial_seed()) * 0x9E3779B97F4A7C15 + off * 0xD1B54A32D192ED03 + 1) & (2 ** 62 - 1)
 
 
 def apply_ops(batch: torch.Tensor, ops: Sequence[int], shift: int = 0, freq: tuple = (0, 0), time: tuple = (0, 0),
@@ -61,7 +68,7 @@ def time_shift(audio, shift_range=0.1):
 
 def add_noise(audio, noise_level=0.005):
     """ViT_engine.py:44-47."""
-    return apply_ops(audio, [NOISE], noise_level=noise_level, noise_seed=_noise_seed())
+    return apply_ops(audio, [NOISE], noise_level=noise_level, noise_seed=_noise_seed(audio))
 
 
 def _draw_mask(dim, max_width):
@@ -130,11 +137,13 @@ def draw_augmentation(shape, augment_prob=0.5):
 
 def augment_batch(batch, augment_prob=0.5, normalize_ref_db: Optional[float] = None):
     """ViT_engine.py:81-93, one fused pass; ``normalize_ref_db`` additionally fuses the db_normalize the engine applies
-    next (ViT_engine.py:284-287)."""
+    next (ViT_engine.py:284-287).  Returns a NEW tensor: the reference's frequency_mask / time_mask write into the caller's
+    batch in place and return it (ViT_engine.py:57-79); the returned values are the same, the side effect on ``batch`` is
+    deliberately not reproduced."""
     plan = draw_augmentation(tuple(batch.shape), augment_prob)
     if not plan["ops"] and normalize_ref_db is None:
         return batch
-    seed = _noise_seed() if NOISE in plan["ops"] else 0
+    seed = _noise_seed(batch) if NOISE in plan["ops"] else 0
     return apply_ops(batch, noise_seed=seed, normalize_ref_db=normalize_ref_db, **plan)
 
 

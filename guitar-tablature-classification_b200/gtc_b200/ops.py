@@ -24,11 +24,20 @@ def _stream() -> C.c_void_p:
 
 
 def _need_cuda(*ts: torch.Tensor) -> None:
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.GtcError("libgtc kernels take CUDA tensors only (there is no CPU fallback)")
-        if t is not None and not t.is_contiguous():
+        if not t.is_contiguous():
             raise _lib.GtcError("libgtc kernels take contiguous tensors")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            # the launch goes to the CURRENT device's stream: a tensor of another GPU would be read through a foreign pointer
+            raise _lib.GtcError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur} "
+                                "(wrap the call in torch.cuda.device(tensor.device))")
 
 
 def segment_counts(clip_lens: Sequence[int], seg_len: int, seg_hop: int) -> np.ndarray:
@@ -325,6 +334,9 @@ def patches(db: torch.Tensor, index: Optional[torch.Tensor] = None, img_size=(22
     h, w = int(img_size[0]), int(img_size[1])
     if out is None:
         out = torch.empty((n, 3, h, w), dtype=torch.float32, device=db.device)
+    if tuple(out.shape) != (n, 3, h, w) or out.dtype != torch.float32 or out.device != db.device:
+        raise _lib.GtcError(f"patches: out must be float32 {(n, 3, h, w)} on {db.device}, got {out.dtype} {tuple(out.shape)} on {out.device}")
+    _need_cuda(out)
     _lib.check(_lib.load().gtc_patches(_ptr(db), _ptr(index), n, db.shape[1], db.shape[2], h, w, int(mode), _ptr(out),
                                        _stream()), "gtc_patches")
     return out

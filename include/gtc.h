@@ -34,12 +34,11 @@ extern "C" {
 #define GTC_E_NOMEM    -3   /* workspace too small / allocation      */
 #define GTC_E_UNSUP    -4   /* unsupported configuration             */
 
-/* GEMM engines for the segment operator contraction */
-#define GTC_GEMM_TCGEN05_3XTF32  0   /* TMA + tcgen05.mma kind::tf32, hi/lo split, fp32 TMEM accumulators            */
-#define GTC_GEMM_SIMT_FP32       1   /* CUDA-core fp32 FMA tiles (validation engine for the tensor-core path)       */
-
-#define GTC_GEMM_TCGEN05_FP16X2  2   /* TMA + tcgen05.mma kind::f16 on power-of-two scaled fp16 hi/lo pairs (22 mantissa bits): half the
-                                        tensor time and operand bytes of 3xTF32; needs |audio| < 256 (default of the Python host)     */
+/* GEMM engines for the segment operator contraction (the Python host's default is GTC_GEMM_TCGEN05_FP16X2) */
+#define GTC_GEMM_TCGEN05_FP16X2  2   /* DEFAULT.  TMA + tcgen05.mma kind::f16 on power-of-two scaled fp16 hi/lo pairs (22 mantissa bits):
+                                        half the tensor time and operand bytes of 3xTF32; needs |audio| < 256                        */
+#define GTC_GEMM_TCGEN05_3XTF32  0   /* TMA + tcgen05.mma kind::tf32, tf32 hi + fp32 lo split, fp32 TMEM accumulators                */
+#define GTC_GEMM_SIMT_FP32       1   /* CUDA-core fp32 FMA tiles (validation engine for the tensor-core paths)                       */
 
 /* patch modes */
 #define GTC_PATCH_VIT  0   /* ViT_dataloader.py:31-51  : (x+120)/120, clip, bicubic, 3 identical channels            */
