@@ -71,6 +71,47 @@ def save_label(path, tab: np.ndarray) -> None:
     np.save(path, np.ascontiguousarray(tab, dtype=np.int8))
 
 
+_HEADER_CACHE: dict = {}
+
+
+def _npy_header(shape, dtype, fortran: bool) -> bytes:
+    """The exact header bytes np.save writes for an array of this shape / dtype / order (format 1.0)."""
+    key = (tuple(shape), np.dtype(dtype).str, bool(fortran))
+    h = _HEADER_CACHE.get(key)
+    if h is None:
+        import io
+        buf = io.BytesIO()
+        np.save(buf, np.zeros(shape, dtype=dtype, order="F" if fortran else "C"))
+        raw = buf.getvalue()
+        h = raw[: len(raw) - int(np.prod(shape)) * np.dtype(dtype).itemsize]
+        _HEADER_CACHE[key] = h
+    return h
+
+
+def save_features_exploded(out_dir, base_name: str, feats: np.ndarray, first: int = 0) -> int:
+    """The per-segment files of cqt.py:61-63 for one clip -- ``{base}_segment_{k}.npy``, (n_bins, T) '<f4' Fortran order --
+    byte for byte what ``save_feature`` / ``np.save`` writes, without building 10 array objects and headers per second of
+    audio: one transposed copy of the clip's block, one cached header, one write per file."""
+    import os
+    feats = np.asarray(feats, dtype=np.float32)
+    if feats.ndim != 3 or len(feats) == 0:
+        return 0
+    n, nb, T = feats.shape
+    header = _npy_header((nb, T), np.float32, True)
+    data = np.ascontiguousarray(feats.transpose(0, 2, 1))            # C order of (T, n_bins) == Fortran order of (n_bins, T)
+    raw = memoryview(data).cast("B")
+    step = nb * T * 4
+    prefix = os.path.join(out_dir, base_name + "_segment_")
+    flags = os.O_WRONLY | os.O_CREAT | os.O_TRUNC
+    for k in range(n):                                               # open + one gathered write + close: 13 us per file on tmpfs
+        fd = os.open(f"{prefix}{first + k}.npy", flags, 0o666)
+        try:
+            os.writev(fd, (header, raw[k * step: (k + 1) * step]))
+        finally:
+            os.close(fd)
+    return n
+
+
 # ---------------------------------------------------------------------------------------------------- packed files
 
 FEATURE_PACK_SUFFIX = "_segments.npy"      # {base}_segments.npy       <->  {base}_segment_{k}.npy      (cqt.py:62)
