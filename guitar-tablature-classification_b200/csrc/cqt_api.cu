@@ -112,11 +112,21 @@ extern "C" int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int 
   p.kp = (int)round_up(p.row_len, p.kb_elems);
   p.k_total = p.parts * p.kp;
   p.n_out = 2 * n_bins * n_frames;
-  p.n_pad = (int)round_up(p.n_out, 128);
   p.engine = gemm_engine;
+  // N tile width and operator row order (OpLayout, gtc_common.cuh): the widest tile of whole bins x all frames that the
+  // tensor core takes (N <= 256, N % 16 == 0) and that tiles the bins exactly; else plain bin-major rows.
+  p.bins_per_tile = 0;
+  p.nc = tc_pick_plain_width(p.n_out);
+  for (int b = 256 / (2 * n_frames); b >= 1 && tensor; --b)
+    if ((2 * n_frames * b) % 16 == 0 && n_bins % b == 0 && tc_has_frame_major_kernel(2 * n_frames * b, n_frames)) {
+      p.bins_per_tile = b;
+      p.nc = 2 * n_frames * b;
+      break;
+    }
+  p.n_pad = (int)round_up(round_up(p.n_out, p.nc), 128);      // whole tiles, and the SIMT engine's 128-row blocks
   p.sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("GTC_TC_KSPLIT")) p.tc_kb_per_split = atoi(e);
-  p.tc_fuse_finish = 0;                                 // measured slower than the separate pass, see cqt_gemm_tc.cu
+  p.tc_fuse_finish = 1;                                 // dB finish inside the GEMM epilogue (cqt_gemm_tc.cu); 0 = separate pass
   if (const char* e = getenv("GTC_FUSE_FINISH")) p.tc_fuse_finish = atoi(e) != 0;
   if (tensor && (p.n_out % 16 != 0)) {
     delete plan;
@@ -132,6 +142,12 @@ extern "C" int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int 
     return GTC_OK;
   };
   auto at_of = [&](int j) { const int part = j / p.row_len; return (size_t)part * p.kp + (j - part * p.row_len); };
+  // host row (t * n_bins + bin) * 2 + c  ->  library row (OpLayout)
+  const OpLayout lay = op_layout(p);
+  std::vector<int> lib_row(p.n_out);
+  for (int t = 0; t < n_frames; ++t)
+    for (int b = 0; b < n_bins; ++b)
+      for (int c = 0; c < 2; ++c) lib_row[(t * n_bins + b) * 2 + c] = lay.gemm_row(b, t, c);
   if (half) {
     // fp16x2: A * 2^s = hi + lo with s such that max|A| * 2^s <= 2^13; absolute quantisation error <= 2^-25 (fp16
     // subnormal spacing / 2) against row maxima of ~2^13, i.e. < 2^-36 relative -- see DESIGN.md 3.1
@@ -146,7 +162,7 @@ extern "C" int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int 
     for (int n = 0; n < p.n_out; ++n)
       for (int j = 0; j < seg_len; ++j) {
         const float v = h_operator[(size_t)n * seg_len + j] * a_scale;
-        const size_t at = (size_t)n * p.k_total + at_of(j);
+        const size_t at = (size_t)lib_row[n] * p.k_total + at_of(j);
         hi[at] = __float2half_rn(v);
         lo[at] = __float2half_rn(v - __half2float(hi[at]));
       }
@@ -159,7 +175,7 @@ extern "C" int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int 
     for (int n = 0; n < p.n_out; ++n)
       for (int j = 0; j < seg_len; ++j) {
         const float v = h_operator[(size_t)n * seg_len + j];
-        const size_t at = (size_t)n * p.k_total + at_of(j);
+        const size_t at = (size_t)lib_row[n] * p.k_total + at_of(j);
         raw[at] = v;
         hi[at] = tf32_rn_host(v);
         lo[at] = v - hi[at];

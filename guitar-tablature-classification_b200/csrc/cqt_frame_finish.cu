@@ -147,7 +147,7 @@ int launch_finish_db(const PlanImpl& p, const float* d_mag2, const float* d_rowm
 
 __global__ void __launch_bounds__(256)
 finish_complex_kernel(const float* __restrict__ cplx, const int64_t* __restrict__ seg_off, int n_clips, int parts,
-                      int64_t n_seg, int n_bins, int n_frames, float* __restrict__ out) {
+                      int64_t n_seg, int n_bins, int n_frames, const OpLayout lay, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int n_mag = n_bins * n_frames;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -158,7 +158,7 @@ finish_complex_kernel(const float* __restrict__ cplx, const int64_t* __restrict_
     float2* dst = reinterpret_cast<float2*>(out + g * 2 * n_mag);
     for (int o = lane; o < n_mag; o += 32) {
       const int bin = o / n_frames, t = o - bin * n_frames;
-      dst[o] = src[t * n_bins + bin];
+      dst[o] = src[lay.gemm_row(bin, t, 0) >> 1];        // the GEMM's row order (OpLayout) -> [bin][t]
     }
   }
 }
@@ -169,7 +169,7 @@ int launch_finish_complex(const PlanImpl& p, const float* d_cplx, const int64_t*
   const int64_t cap = (int64_t)p.sm_count * 8;
   if (blocks > cap) blocks = cap;
   finish_complex_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_cplx, d_seg_off, n_clips, p.parts, n_seg, p.n_bins,
-                                                           p.n_frames, d_out);
+                                                           p.n_frames, op_layout(p), d_out);
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;
 }

@@ -158,7 +158,8 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&r)[8]) {
 // the SM beside this one (FrontEnd(coresident=True)).  Measured on B200 (profiles/r01j_coresident.md): co-running the
 // two kernels is SLOWER than back to back -- both live on L2 bandwidth (operator tiles re-read by every M tile here,
 // 7 TB/s of stores there): GEMM+finish 0.36 -> 0.94 ms, patch launch 1.29 -> 1.93 ms per chunk.
-template <int NC, bool kComplex, bool kHalf>
+// TFM > 0: frame-major tiles (OpLayout, gtc_common.cuh) of a TFM-frame recipe: NC = 2 * TFM * bins_per_tile; 0: plain rows.
+template <int NC, bool kComplex, bool kHalf, int TFM>
 __global__ void __maxnreg__(TC_MAXNREG)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo,
@@ -166,6 +167,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   constexpr int H = NC / 2;                  // columns per epilogue warp
   constexpr int EPK = TKB_BYTES / (kHalf ? 2 : 4);   // operand elements per k-block
   static_assert(NC % 16 == 0 && NC <= TMAXN && H % 8 == 0, "unsupported tile width");
+  static_assert(TFM == 0 || NC % (2 * TFM) == 0, "a frame-major tile holds whole bins x TFM frames");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bars[2 * TSTAGES + 4];
   __shared__ uint32_t s_tmem_slot;
@@ -323,27 +325,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             *reinterpret_cast<float4*>(prm.cplx + row * prm.n_out + n0 + c) = make_float4(sum[c], sum[c + 1], sum[c + 2], sum[c + 3]);
       } else {
         float rmax = 0.f;
+        if (TFM == 0) {
 #pragma unroll
-        for (int c = 0; c < H; c += 8) {
-          float m[4];
+          for (int c = 0; c < H; c += 8) {
+            float m[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) m[j] = sum[c + 2 * j] * sum[c + 2 * j] + sum[c + 2 * j + 1] * sum[c + 2 * j + 1];
-          if (n0 + c < prm.n_out) {
-            rmax = fmaxf(fmaxf(rmax, fmaxf(m[0], m[1])), fmaxf(m[2], m[3]));
-            *reinterpret_cast<float4*>(prm.mag2 + row * n_mag + ((n0 + c) >> 1)) = make_float4(m[0], m[1], m[2], m[3]);
+            for (int j = 0; j < 4; ++j) m[j] = sum[c + 2 * j] * sum[c + 2 * j] + sum[c + 2 * j + 1] * sum[c + 2 * j + 1];
+            if (n0 + c < prm.n_out) {
+              rmax = fmaxf(fmaxf(rmax, fmaxf(m[0], m[1])), fmaxf(m[2], m[3]));
+              *reinterpret_cast<float4*>(prm.mag2 + row * n_mag + ((n0 + c) >> 1)) = make_float4(m[0], m[1], m[2], m[3]);
+            }
+          }
+        } else {
+          // frame-major tile: accumulator column j = t * 2B + bin_in_tile * 2 + {re, im}  ->  final column (bin, t)
+          constexpr int B = TFM > 0 ? NC / (2 * TFM) : 1;
+          float* dst = prm.mag2 + row * n_mag + chunk * B * TFM;
+#pragma unroll
+          for (int c = 0; c < H; c += 2) {
+            const int j = half * H + c;
+            const int t = j / (2 * B), bl = (j - t * 2 * B) >> 1;
+            const float m = sum[c] * sum[c] + sum[c + 1] * sum[c + 1];
+            rmax = fmaxf(rmax, m);
+            dst[bl * TFM + t] = m;
           }
         }
         atomicMax(reinterpret_cast<int*>(prm.rowmax + row), __float_as_int(rmax));
-        // ---- optional fused dB finish (cqt.py:56-58; GTC_OPT_FUSE_FINISH, off by default).  The reference level is the
-        //      segment's maximum over ALL its outputs, i.e. over the n_chunks N tiles of this 128-row block, which
-        //      different CTAs compute.  Every tile publishes its |C|^2 and row maxima (fence), then bumps the block's
-        //      counter; the CTA that brings it to n_chunks owns the finished block and converts it (8 warps x 16
-        //      segments, |C|^2 re-read from L2 where it was just written) while its MMA warp runs ahead into the next
-        //      tile (two TMEM stages = two K splits = 12 us of slack).
-        //      Measured on B200 (profiles/r01k_fused_finish.md): 0.58 ms per 18 900-row chunk against 0.35 ms for
-        //      GEMM + the separate finish_db_kernel.  The re-reads queue behind the TMA operand stream that keeps this
-        //      SM's L2 port busy, a block costs ~60 us instead of the 12 us of slack, and the stall repeats every wave;
-        //      the stand-alone pass spreads the same 36 MB over all SMs with nothing else in flight (28 us).
+        // ---- fused dB finish (cqt.py:56-58; GTC_OPT_FUSE_FINISH, default on).  The reference level of a segment is its
+        //      maximum over ALL its outputs, i.e. over the n_chunks N tiles of this 128-row block, which different CTAs
+        //      compute.  Every tile publishes its |C|^2 and row maxima (fence), then bumps the block's counter; the CTA
+        //      that brings it to n_chunks owns the finished block and converts it while its MMA warp runs ahead into
+        //      the next tile (two TMEM stages = two K splits of slack).  Nobody waits for anybody, so co-scheduling of
+        //      the CTAs is not assumed.  |C|^2 is already in the final [bin][t] order (OpLayout), so the conversion is a
+        //      straight 16-byte read of the L2-resident block with 16 loads in flight per thread: ~8 us per block.
+        //      (The first version re-read |C|^2 through a [t][bin] -> [bin][t] transposing gather, one L2 round trip per
+        //      row: 60 us per block, slower than the separate finish kernel -- profiles/r01k_fused_finish.md.)
         if (prm.fin.out_db != nullptr) {
           const FinishArgs& f = prm.fin;
           __threadfence();
@@ -352,10 +367,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
           if (s_block_done) {
             __threadfence();
-            const int n_mag = f.n_bins * f.n_frames;
-            // clip of the block's first row (rows of clip c start at seg_off[c] + c*(P-1)); later rows only step forward
+            const int n_mag_f = f.n_bins * f.n_frames;
+            // clip of the warp's first row (rows of clip c start at seg_off[c] + c*(P-1)); later rows only step forward
             int c = 0;
-            int64_t row_lo = 0, row_hi = 0, seg_hi = 0;              // clip c owns rows [row_lo, row_hi), segments < seg_hi
+            int64_t row_hi = 0, seg_hi = 0;                          // clip c owns rows < row_hi, segments < seg_hi
             {
               const int64_t r0 = m_tile * TBM + (warp - 2);
               int lo = 0, hi = f.n_clips;
@@ -364,23 +379,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                 if (__ldg(f.seg_off + mid) + (int64_t)mid * (f.parts - 1) <= r0) lo = mid; else hi = mid;
               }
               c = lo;
-              row_lo = __ldg(f.seg_off + c) + (int64_t)c * (f.parts - 1);
               seg_hi = __ldg(f.seg_off + c + 1);
               row_hi = seg_hi + (int64_t)(c + 1) * (f.parts - 1);
             }
-            for (int i = warp - 2; i < TBM; i += TC_EPI_WARPS) {
-              const int64_t r = m_tile * TBM + i;
-              if (r >= f.n_rows) break;
-              while (r >= row_hi && c + 1 < f.n_clips) {
-                ++c;
-                row_lo = row_hi;
-                seg_hi = __ldg(f.seg_off + c + 1);
-                row_hi = seg_hi + (int64_t)(c + 1) * (f.parts - 1);
+            constexpr int RG = 2;                                    // rows in flight per warp (x 4 vectors per lane)
+            for (int i0 = warp - 2; i0 < TBM; i0 += TC_EPI_WARPS * RG) {
+              int64_t seg[RG];
+#pragma unroll
+              for (int k = 0; k < RG; ++k) {
+                const int64_t r = m_tile * TBM + i0 + TC_EPI_WARPS * k;
+                seg[k] = -1;
+                if (r < f.n_rows) {
+                  while (r >= row_hi && c + 1 < f.n_clips) {
+                    ++c;
+                    seg_hi = __ldg(f.seg_off + c + 1);
+                    row_hi = seg_hi + (int64_t)(c + 1) * (f.parts - 1);
+                  }
+                  const int64_t g = r - (int64_t)c * (f.parts - 1);  // the clip's last P-1 rows start no segment
+                  if (g < seg_hi) seg[k] = g;
+                }
               }
-              const int64_t g = r - (int64_t)c * (f.parts - 1);      // the clip's last P-1 rows start no segment
-              if (g >= seg_hi) continue;
-              finish_row_db(prm.mag2 + r * n_mag, __ldcg(prm.rowmax + r), f.out_db + g * n_mag, lane, f.n_bins, f.n_frames,
-                            f.power, f.amin, f.top_db, f.cut_db, f.floor_db);
+              if ((n_mag_f & 3) == 0) {
+                const int nv = n_mag_f >> 2;
+                for (int ob = 0; ob < nv; ob += 128) {
+                  float4 v[RG][4];
+                  float ref[RG];
+#pragma unroll
+                  for (int k = 0; k < RG; ++k) {
+                    const int64_t r = m_tile * TBM + i0 + TC_EPI_WARPS * k;
+                    ref[k] = seg[k] >= 0 ? __ldcg(prm.rowmax + r) : 0.f;
+                    const float4* s4 = reinterpret_cast<const float4*>(prm.mag2 + r * n_mag_f);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                      const int o = ob + lane + 32 * u;
+                      v[k][u] = (seg[k] >= 0 && o < nv) ? __ldcg(s4 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                  }
+#pragma unroll
+                  for (int k = 0; k < RG; ++k) {
+                    if (seg[k] < 0) continue;
+                    const DbScale scale(ref[k], f.power, f.amin, f.top_db, f.cut_db, f.floor_db);
+                    float4* d4 = reinterpret_cast<float4*>(f.out_db + seg[k] * n_mag_f);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                      const int o = ob + lane + 32 * u;
+                      if (o < nv) d4[o] = make_float4(scale(v[k][u].x), scale(v[k][u].y), scale(v[k][u].z), scale(v[k][u].w));
+                    }
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < RG; ++k) {
+                  const int64_t r = m_tile * TBM + i0 + TC_EPI_WARPS * k;
+                  if (seg[k] >= 0)
+                    finish_row_db(prm.mag2 + r * n_mag_f, __ldcg(prm.rowmax + r), f.out_db + seg[k] * n_mag_f, lane, f.n_bins,
+                                  f.n_frames, f.power, f.amin, f.top_db, f.cut_db, f.floor_db);
+                }
+              }
             }
             if (warp == 2 && lane == 0) f.tile_done[m_tile] = 0;     // ready for the next contraction over this workspace
           }
@@ -432,56 +487,63 @@ static int encode_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t 
   return GTC_OK;
 }
 
-static const int kTileWidths[] = {256, 240, 192, 128, 64};
+// Kernel instantiations: plain row order for a few tile widths, frame-major tiles (NC = 2 * T * bins_per_tile) for the
+// recipes in use: T = 5 (22.05 kHz, cqt.py recipe: 24 bins x 5 frames x 2 = 240) and T = 9 (44.1 kHz: 8 x 9 x 2 = 144).
+static const int kPlainWidths[] = {256, 192, 128, 64};
 
-static int pick_nc(int n_out) {
-  for (int nc : kTileWidths)
+int tc_pick_plain_width(int n_out) {
+  for (int nc : kPlainWidths)
     if (n_out % nc == 0) return nc;
   return 256;                       // ragged: TMA zero-fills operator rows beyond n_pad, stores are guarded
 }
 
-template <int NC>
-static int set_smem_attr() {
-  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<NC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<NC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<NC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<NC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-  return GTC_OK;
+bool tc_has_frame_major_kernel(int nc, int n_frames) { return (nc == 240 && n_frames == 5) || (nc == 144 && n_frames == 9); }
+
+// calls f(kernel) for the four (complex, half) variants of one (NC, TFM), or for the selected one
+template <int NC, int TFM, typename F>
+static int for_variant(int cplx /* -1 = all */, int half, F&& f) {
+  int rc = GTC_OK;
+  if ((cplx < 0 || cplx == 0) && (half < 0 || half == 0) && rc == GTC_OK) rc = f(gemm_tc_kernel<NC, false, false, TFM>);
+  if ((cplx < 0 || cplx == 1) && (half < 0 || half == 0) && rc == GTC_OK) rc = f(gemm_tc_kernel<NC, true, false, TFM>);
+  if ((cplx < 0 || cplx == 0) && (half < 0 || half == 1) && rc == GTC_OK) rc = f(gemm_tc_kernel<NC, false, true, TFM>);
+  if ((cplx < 0 || cplx == 1) && (half < 0 || half == 1) && rc == GTC_OK) rc = f(gemm_tc_kernel<NC, true, true, TFM>);
+  return rc;
+}
+
+template <typename F>
+static int for_plan_kernels(const PlanImpl& p, int cplx, int half, F&& f) {
+  if (p.bins_per_tile > 0) {
+    if (p.nc == 240 && p.n_frames == 5) return for_variant<240, 5>(cplx, half, f);
+    if (p.nc == 144 && p.n_frames == 9) return for_variant<144, 9>(cplx, half, f);
+    set_error("no frame-major tensor-core kernel for tile %d x %d frames", p.nc, p.n_frames);
+    return GTC_E_UNSUP;
+  }
+  switch (p.nc) {
+    case 256: return for_variant<256, 0>(cplx, half, f);
+    case 192: return for_variant<192, 0>(cplx, half, f);
+    case 128: return for_variant<128, 0>(cplx, half, f);
+    case 64: return for_variant<64, 0>(cplx, half, f);
+    default: set_error("no tensor-core kernel for tile width %d", p.nc); return GTC_E_UNSUP;
+  }
 }
 
 int tc_plan_init(PlanImpl& p) {
   CUtensorMap* maps = new CUtensorMap[2];
   p.tmap_op_hi = &maps[0];
   p.tmap_op_lo = &maps[1];
-  const int nc = pick_nc(p.n_out);
-  int rc = encode_2d(&maps[0], p.d_op_hi, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)nc, p.elem_bytes);
+  int rc = encode_2d(&maps[0], p.d_op_hi, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)p.nc, p.elem_bytes);
   if (rc != GTC_OK) return rc;
-  rc = encode_2d(&maps[1], p.d_op_lo, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)nc, p.elem_bytes);
+  rc = encode_2d(&maps[1], p.d_op_lo, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)p.nc, p.elem_bytes);
   if (rc != GTC_OK) return rc;
-  switch (nc) {
-    case 256: return set_smem_attr<256>();
-    case 240: return set_smem_attr<240>();
-    case 192: return set_smem_attr<192>();
-    case 128: return set_smem_attr<128>();
-    default: return set_smem_attr<64>();
-  }
+  return for_plan_kernels(p, -1, -1, [](auto kern) -> int {
+    GTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    return GTC_OK;
+  });
 }
 
 void tc_plan_free(PlanImpl& p) {
   if (p.tmap_op_hi) delete[] reinterpret_cast<CUtensorMap*>(p.tmap_op_hi);
   p.tmap_op_hi = p.tmap_op_lo = nullptr;
-}
-
-template <int NC>
-static void launch_nc(bool cplx, bool half, unsigned grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b,
-                      const CUtensorMap& c, const CUtensorMap& d, const TcParams& prm) {
-  if (half) {
-    if (cplx) gemm_tc_kernel<NC, true, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, c, d, prm);
-    else      gemm_tc_kernel<NC, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, c, d, prm);
-  } else {
-    if (cplx) gemm_tc_kernel<NC, true, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, c, d, prm);
-    else      gemm_tc_kernel<NC, false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, c, d, prm);
-  }
 }
 
 int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int64_t n_rows_pad, int64_t n_rows_alloc,
@@ -493,7 +555,7 @@ int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int6
   rc = encode_2d(&tm_xlo, d_xlo, (uint64_t)n_rows_alloc, (uint64_t)p.kp, TBM, p.elem_bytes);
   if (rc != GTC_OK) return rc;
   TcParams prm;
-  prm.nc = pick_nc(p.n_out);
+  prm.nc = p.nc;
   prm.kb_per_split = (p.tc_kb_per_split > 0 ? p.tc_kb_per_split : 8) * (128 / TKB_BYTES);   // option counts 128-byte blocks
   prm.n_chunks = (int)ceil_div(p.n_out, prm.nc);
   prm.n_out = p.n_out;
@@ -509,15 +571,11 @@ int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int6
   const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
   const CUtensorMap& tm_ohi = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_hi);
   const CUtensorMap& tm_olo = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_lo);
-  const bool cplx = d_cplx != nullptr;
-  const bool half = p.elem_bytes == 2;
-  switch (prm.nc) {
-    case 256: launch_nc<256>(cplx, half, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
-    case 240: launch_nc<240>(cplx, half, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
-    case 192: launch_nc<192>(cplx, half, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
-    case 128: launch_nc<128>(cplx, half, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
-    default:  launch_nc<64>(cplx, half, grid, st, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm); break;
-  }
+  rc = for_plan_kernels(p, d_cplx != nullptr ? 1 : 0, p.elem_bytes == 2 ? 1 : 0, [&](auto kern) -> int {
+    kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
+    return GTC_OK;
+  });
+  if (rc != GTC_OK) return rc;
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;
 }

@@ -93,28 +93,53 @@ struct DbScale {
   }
 };
 
-// one warp: src = the segment's |C|^2 as [t][bin] (L2), dst = its dB features as [bin][t].  All of a row's loads are
-// issued before the first value is used (U x 32 elements per trip), so a row costs one L2 round trip, not n_mag / 32.
-template <int U = 16>
+// one warp: src = the segment's |C|^2, dst = its dB features, both [bin][t] (the GEMM's operator rows are ordered so that
+// its |C|^2 output already has the final layout: OpLayout below), 16-byte vectors, all loads issued before the first use.
+template <int U = 4>
 __device__ __forceinline__ void finish_row_db(const float* src, float m2max, float* dst, int lane, int n_bins, int n_frames,
                                               float power, float amin, float top_db, float cut_db, float floor_db) {
   const int n_mag = n_bins * n_frames;
   const DbScale scale(m2max, power, amin, top_db, cut_db, floor_db);
-  for (int o0 = lane; o0 < n_mag; o0 += 32 * U) {
-    float v[U];
+  if ((n_mag & 3) == 0) {
+    const int nv = n_mag >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int o0 = lane; o0 < nv; o0 += 32 * U) {
+      float4 v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int o = o0 + 32 * u;
-      const int bin = o / n_frames, t = o - bin * n_frames;
-      v[u] = o < n_mag ? __ldcg(src + t * n_bins + bin) : 0.f;
-    }
+      for (int u = 0; u < U; ++u) v[u] = (o0 + 32 * u < nv) ? __ldcg(s4 + o0 + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int o = o0 + 32 * u;
-      if (o < n_mag) dst[o] = scale(v[u]);
+      for (int u = 0; u < U; ++u)
+        if (o0 + 32 * u < nv) d4[o0 + 32 * u] = make_float4(scale(v[u].x), scale(v[u].y), scale(v[u].z), scale(v[u].w));
     }
+  } else {
+    for (int o = lane; o < n_mag; o += 32) dst[o] = scale(__ldcg(src + o));
   }
 }
+
+// ---- operator row order.  The host hands the operator over with rows (t * n_bins + bin) * 2 + {re, im} (gtc.h); inside
+// the library the rows are re-ordered so that (a) the GEMM's |C|^2 output column of (bin, t) is bin * T + t, the final
+// [bin][t] feature layout (cqt.py:58 saves (n_bins, T)), and (b) where the tile width allows it, an N tile holds
+// `bins_per_tile` whole bins ordered FRAME-major inside the tile:
+//     gemm row = tile * nc + t * (2 * bins_per_tile) + bin_in_tile * 2 + c,     tile = bin / bins_per_tile
+// so that the rows of one frame are one contiguous column range of the accumulator -- a frame's operator rows are non-zero
+// only on a window of samples around the frame, and the tensor-core engine multiplies a k-block only with the frames
+// whose window reaches it (cqt_gemm_tc.cu).  bins_per_tile == 0: plain order, gemm row = (bin * T + t) * 2 + c.
+struct OpLayout {
+  int nc, bins_per_tile, n_bins, n_frames;
+  __host__ __device__ __forceinline__ int gemm_row(int bin, int t, int c) const {
+    if (bins_per_tile == 0) return (bin * n_frames + t) * 2 + c;
+    const int tile = bin / bins_per_tile, bl = bin - tile * bins_per_tile;
+    return tile * nc + t * 2 * bins_per_tile + bl * 2 + c;
+  }
+  // final |C|^2 column (bin * T + t) of the pair of gemm rows (n, n + 1), n even
+  __host__ __device__ __forceinline__ int mag_col(int n) const {
+    if (bins_per_tile == 0) return n >> 1;
+    const int tile = n / nc, j = n - tile * nc;
+    const int t = j / (2 * bins_per_tile), bl = (j - t * 2 * bins_per_tile) >> 1;
+    return (tile * bins_per_tile + bl) * n_frames + t;
+  }
+};
 
 // ---- segment-operator plan (cqt_api.cu) -------------------------------------------------------------------
 struct PlanImpl {
@@ -128,11 +153,13 @@ struct PlanImpl {
   int k_total;      // P * kp
   int n_out;        // 2 * n_bins * n_frames  (real operator rows)
   int n_pad;        // n_out rounded up to 128
+  int nc;           // N tile width of the tensor-core engines (operator rows per tile)
+  int bins_per_tile;   // > 0: tiles hold whole bins, frame-major inside the tile (OpLayout); 0: plain bin-major rows
   int engine;
   int sm_count;
   int tc_max_ctas;      // persistent GEMM grid limit (0 = sm_count)
   int tc_kb_per_split;  // K blocks per tensor-core accumulation split (0 = default), env GTC_TC_KSPLIT
-  int tc_fuse_finish;   // 1: the tcgen05 epilogue also does the dB finish (GTC_OPT_FUSE_FINISH; default 0, measured slower)
+  int tc_fuse_finish;   // 1: the tcgen05 epilogue also does the dB finish (GTC_OPT_FUSE_FINISH; default 1)
   float x_scale;    // fp16x2 engine: audio is multiplied by this power of two before the hi/lo split (1 otherwise)
   float out_scale;  // epilogue factor undoing x_scale and the operator's power-of-two scale (1 otherwise)
   float* d_op;      // [n_pad][k_total]  operator, fp32, K padded per part (SIMT engine only)
@@ -146,11 +173,14 @@ struct PlanImpl {
 int launch_frame(const PlanImpl& p, const void* d_audio, int pcm16, const int64_t* d_clip_off, const int64_t* d_seg_off,
                  int n_clips, int64_t n_rows, int64_t n_rows_alloc, void* d_xhi, void* d_xlo, float* d_rowmax,
                  int* d_tile_done, cudaStream_t st);
+inline OpLayout op_layout(const PlanImpl& p) { return OpLayout{p.nc, p.bins_per_tile, p.n_bins, p.n_frames}; }
 int launch_gemm_simt(const PlanImpl& p, const float* d_xhi, const float* d_xlo, int64_t n_rows_pad,
                      float* d_mag2, float* d_cplx, float* d_rowmax, cudaStream_t st);
 int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int64_t n_rows_pad, int64_t n_rows_alloc,
                    float* d_mag2, float* d_cplx, float* d_rowmax, const FinishArgs& fin, cudaStream_t st);
 int tc_plan_init(PlanImpl& p);
+int tc_pick_plain_width(int n_out);                       // tile width of the plain row order
+bool tc_has_frame_major_kernel(int nc, int n_frames);     // is gemm_tc_kernel instantiated for this frame-major tile?
 void tc_plan_free(PlanImpl& p);
 int launch_finish_db(const PlanImpl& p, const float* d_mag2, const float* d_rowmax, const int64_t* d_seg_off,
                      int n_clips, int64_t n_seg, float* d_out_db, float power, float amin, float top_db, float cut_db,

@@ -84,7 +84,11 @@ def stream_corpus(n_clips: int, clip_seconds: float, rank: int = 0, world_size: 
     for c0 in range(0, len(mine), clips_per_block):
         ids = mine[c0:c0 + clips_per_block]
         audio = device_corpus_block(ids, n_samples, sr, dev, plucks_per_s)
-        on, du, pi, evt_off = synth.note_events([clip_seconds] * len(ids), seed=7919 * int(ids[0]) + 2)
+        # note events are a function of the CLIP id alone (like the audio), so any sharding of the corpus rasterises the
+        # same labels and the gathered stats of N ranks equal the serial sums (jam_to_tablature.py:376-378)
+        per_clip = [synth.note_events([clip_seconds], seed=7919 * int(cid) + 2) for cid in ids]
+        on, du, pi = (np.concatenate([e[j] for e in per_clip]) for j in range(3))
+        evt_off = np.concatenate([[0], np.cumsum([len(e[0]) for e in per_clip])]).astype(np.int64)
         events = torch.from_numpy(np.stack([on, du, pi])).to(dev)
         inp = ShardInputs(audio, np.full(len(ids), n_samples, dtype=np.int64), events, evt_off, sr=sr)
         torch.cuda.synchronize(dev)
