@@ -38,7 +38,7 @@ static inline float tf32_rn_host(float x) {
 
 struct Workspace {
   int64_t n_rows, n_rows_pad, n_rows_alloc;
-  size_t off_xhi, off_xlo, off_out, off_rowmax, off_done, total;
+  size_t off_xhi, off_xlo, off_out, off_rowmax, off_done, off_segrow, total;
 };
 
 static Workspace workspace_layout(const PlanImpl& p, int64_t n_seg, int64_t n_clips, bool complex_out) {
@@ -55,6 +55,7 @@ static Workspace workspace_layout(const PlanImpl& p, int64_t n_seg, int64_t n_cl
   w.off_out = take(obytes);
   w.off_rowmax = take((size_t)w.n_rows_pad * sizeof(float));
   w.off_done = take((size_t)(w.n_rows_pad / 128) * sizeof(int));      // row-block counters of the fused dB finish
+  w.off_segrow = take((size_t)w.n_rows_pad * sizeof(int));            // operand row -> segment it starts (or -1)
   w.total = o;
   return w;
 }
@@ -126,7 +127,7 @@ extern "C" int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int 
   p.n_pad = (int)round_up(round_up(p.n_out, p.nc), 128);      // whole tiles, and the SIMT engine's 128-row blocks
   p.sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("GTC_TC_KSPLIT")) p.tc_kb_per_split = atoi(e);
-  p.tc_fuse_finish = 1;                                 // dB finish inside the GEMM epilogue (cqt_gemm_tc.cu); 0 = separate pass
+  p.tc_fuse_finish = 0;                                 // 1 = dB finish inside the GEMM epilogue (measured slower, cqt_gemm_tc.cu)
   if (const char* e = getenv("GTC_FUSE_FINISH")) p.tc_fuse_finish = atoi(e) != 0;
   if (tensor && (p.n_out % 16 != 0)) {
     delete plan;
@@ -248,8 +249,10 @@ static int run_segments(const gtc_plan* plan, const void* d_audio, const int64_t
   float* gout = reinterpret_cast<float*>(ws + w.off_out);
   float* rowmax = reinterpret_cast<float*>(ws + w.off_rowmax);
   int* tile_done = reinterpret_cast<int*>(ws + w.off_done);
+  int* seg_of_row = reinterpret_cast<int*>(ws + w.off_segrow);
+  GTC_REQUIRE(n_seg < ((int64_t)1 << 31), GTC_E_UNSUP, "gtc_cqt_segments: more than 2^31 segments in one call");
   int rc = GTC_OK;
-  if (stages & 1) rc = launch_frame(p, d_audio, pcm16, d_clip_off, d_seg_off, (int)n_clips, w.n_rows, w.n_rows_alloc, xhi, xlo, rowmax, tile_done, st);
+  if (stages & 1) rc = launch_frame(p, d_audio, pcm16, d_clip_off, d_seg_off, (int)n_clips, w.n_rows, w.n_rows_alloc, xhi, xlo, rowmax, tile_done, seg_of_row, st);
   if (rc != GTC_OK || (stages & 2) == 0) return rc;
   float* mag2 = complex_out ? nullptr : gout;
   float* cplx = complex_out ? gout : nullptr;
@@ -257,7 +260,7 @@ static int run_segments(const gtc_plan* plan, const void* d_audio, const int64_t
   memset(&fin, 0, sizeof(fin));
   const bool fused = p.engine != GTC_GEMM_SIMT_FP32 && !complex_out && p.tc_fuse_finish;
   if (fused) {
-    fin.out_db = d_out; fin.seg_off = d_seg_off; fin.tile_done = tile_done;
+    fin.out_db = d_out; fin.seg_off = d_seg_off; fin.tile_done = tile_done; fin.seg_of_row = seg_of_row;
     fin.n_clips = (int)n_clips; fin.parts = p.parts; fin.n_bins = p.n_bins; fin.n_frames = p.n_frames;
     fin.n_rows = w.n_rows; fin.n_seg = n_seg;
     fin.power = power; fin.amin = amin; fin.top_db = top_db; fin.cut_db = cut_db; fin.floor_db = floor_db;
@@ -268,7 +271,7 @@ static int run_segments(const gtc_plan* plan, const void* d_audio, const int64_t
     rc = launch_gemm_simt(p, (const float*)xhi, (const float*)xlo, w.n_rows_pad, mag2, cplx, rowmax, st);
   if (rc != GTC_OK || fused) return rc;
   if (complex_out) return launch_finish_complex(p, cplx, d_seg_off, (int)n_clips, n_seg, d_out, st);
-  return launch_finish_db(p, mag2, rowmax, d_seg_off, (int)n_clips, n_seg, d_out, power, amin, top_db, cut_db, floor_db, st);
+  return launch_finish_db(p, mag2, rowmax, seg_of_row, w.n_rows, d_out, power, amin, top_db, cut_db, floor_db, st);
 }
 
 extern "C" int gtc_cqt_segments_db(const gtc_plan* plan, const float* d_audio, const int64_t* d_clip_off,

@@ -21,6 +21,7 @@
 //                              values) stored straight to global memory
 // The second audio row of a segment (hop = window/2, cqt.py:26-27) is just the TMA row coordinate + p.
 #include <cuda.h>
+#include <type_traits>
 #include "gtc_common.cuh"
 
 namespace gtc {
@@ -39,7 +40,7 @@ constexpr uint32_t TC_SMEM_BYTES = TSTAGES * STAGE_BYTES + 1024 /*align slack*/;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 #ifndef TC_MAXNREG
-#define TC_MAXNREG 168
+#define TC_MAXNREG 168     // 10 warps = 3 on the fullest SM sub-partition (16 384 registers): 3 x 32 x 168 is the most that launches
 #endif
 
 struct TcParams {
@@ -145,6 +146,58 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&r)[8]) {
                : "r"(addr) : "memory");
 }
 
+// dB finish of one completed 128-row block by the 8 epilogue warps of the CTA that completed it (see the call site).
+// Two rows x 4 vectors in flight per lane: the accumulation loop above it runs at the 168-register cap (10 warps = 3 on the
+// fullest SM sub-partition), more rows in flight -- or a non-inlined call -- push ptxas into spilling inside that loop.
+__device__ __forceinline__ void fused_finish_block(const TcParams& prm, int64_t m_tile, int warp, int lane) {
+  const FinishArgs& f = prm.fin;
+  __threadfence();
+  const int n_mag_f = f.n_bins * f.n_frames;
+  constexpr int RG = 2;                                    // rows in flight per warp (x 4 vectors per lane)
+  for (int i0 = warp - 2; i0 < TBM; i0 += TC_EPI_WARPS * RG) {
+    int seg[RG];
+#pragma unroll
+    for (int k = 0; k < RG; ++k) seg[k] = __ldg(f.seg_of_row + m_tile * TBM + i0 + TC_EPI_WARPS * k);   // -1: starts no segment
+    if ((n_mag_f & 3) == 0) {
+      const int nv = n_mag_f >> 2;
+      for (int ob = 0; ob < nv; ob += 128) {
+        float4 v[RG][4];
+        float ref[RG];
+#pragma unroll
+        for (int k = 0; k < RG; ++k) {
+          const int64_t r = m_tile * TBM + i0 + TC_EPI_WARPS * k;
+          ref[k] = seg[k] >= 0 ? __ldcg(prm.rowmax + r) : 0.f;
+          const float4* s4 = reinterpret_cast<const float4*>(prm.mag2 + r * n_mag_f);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int o = ob + lane + 32 * u;
+            v[k][u] = (seg[k] >= 0 && o < nv) ? __ldcg(s4 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < RG; ++k) {
+          if (seg[k] < 0) continue;
+          const DbScale scale(ref[k], f.power, f.amin, f.top_db, f.cut_db, f.floor_db);
+          float4* d4 = reinterpret_cast<float4*>(f.out_db + (int64_t)seg[k] * n_mag_f);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int o = ob + lane + 32 * u;
+            if (o < nv) d4[o] = make_float4(scale(v[k][u].x), scale(v[k][u].y), scale(v[k][u].z), scale(v[k][u].w));
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < RG; ++k) {
+        const int64_t r = m_tile * TBM + i0 + TC_EPI_WARPS * k;
+        if (seg[k] >= 0)
+          finish_row_db(prm.mag2 + r * n_mag_f, __ldcg(prm.rowmax + r), f.out_db + (int64_t)seg[k] * n_mag_f, lane, f.n_bins,
+                        f.n_frames, f.power, f.amin, f.top_db, f.cut_db, f.floor_db);
+      }
+    }
+  }
+}
+
 // NC = operator rows per tile (tcgen05.mma N).  Each of the 8 epilogue warps owns 32 rows x NC/2 columns and keeps
 // their running sums in registers: the tensor core adds into its TMEM accumulator with truncation (RZ), which over
 // the ~1650 accumulator updates of a full K pass biases the result by ~3e-5 relative -- measured on B200 -- so K is
@@ -153,17 +206,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&r)[8]) {
 // kHalf: operands are fp16 hi/lo pairs (kind::f16, 64 elements per 128-byte k-block, 16 per MMA) instead of tf32 pairs
 // (kind::tf32, 32 per k-block, 8 per MMA); in bytes the tiles, the swizzle and the +32 B k-step are identical.
 //
-// Register cap (TC_MAXNREG, default 168 = what ptxas picks for 320 threads/SM, no spills).  Building with
-// -DTC_MAXNREG=152 gives 48 640 registers per CTA, so that one 224-thread x 72-register patch CTA (patches.cu) fits on
-// the SM beside this one (FrontEnd(coresident=True)).  Measured on B200 (profiles/r01j_coresident.md): co-running the
-// two kernels is SLOWER than back to back -- both live on L2 bandwidth (operator tiles re-read by every M tile here,
-// 7 TB/s of stores there): GEMM+finish 0.36 -> 0.94 ms, patch launch 1.29 -> 1.93 ms per chunk.
+// Register cap TC_MAXNREG: the CTA owns the SM (184 KB of shared memory), so the cap is simply what 320 threads can have.
+// (r01 experiment: -DTC_MAXNREG=152 lets one 224-thread x 72-register patch CTA (patches.cu) fit beside this one; co-running
+// the two kernels measured SLOWER than back to back -- both live on L2 bandwidth -- profiles/r01j_coresident.md.)
 // TFM > 0: frame-major tiles (OpLayout, gtc_common.cuh) of a TFM-frame recipe: NC = 2 * TFM * bins_per_tile; 0: plain rows.
 template <int NC, bool kComplex, bool kHalf, int TFM>
 __global__ void __maxnreg__(TC_MAXNREG)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo,
-               const TcParams prm) {
+               const __grid_constant__ TcParams prm) {
   constexpr int H = NC / 2;                  // columns per epilogue warp
   constexpr int EPK = TKB_BYTES / (kHalf ? 2 : 4);   // operand elements per k-block
   static_assert(NC % 16 == 0 && NC <= TMAXN && H % 8 == 0, "unsupported tile width");
@@ -292,22 +343,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         const int acc = (int)(it & 1u);
         mbar_wait(bar_tfull(acc), (it >> 1) & 1u);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TMAXN + (uint32_t)(half * H);
+        if (TFM == 0) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TMAXN + (uint32_t)(half * H);
 #pragma unroll
-        for (int c = 0; c + 16 <= H; c += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + c, r);
-          tmem_ld_wait();
+          for (int c = 0; c + 16 <= H; c += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + c, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sum[c + j] = sp == 0 ? __uint_as_float(r[j]) : sum[c + j] + __uint_as_float(r[j]);
-        }
-        if (H % 16) {
-          constexpr int c = H - 8;
-          uint32_t r[8];
-          tmem_ld8(taddr + c, r);
-          tmem_ld_wait();
+            for (int j = 0; j < 16; ++j) sum[c + j] = sp == 0 ? __uint_as_float(r[j]) : sum[c + j] + __uint_as_float(r[j]);
+          }
+          if (H % 16) {
+            constexpr int c = H - 8;
+            uint32_t r[8];
+            tmem_ld8(taddr + c, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) sum[c + j] = sp == 0 ? __uint_as_float(r[j]) : sum[c + j] + __uint_as_float(r[j]);
+            for (int j = 0; j < 8; ++j) sum[c + j] = sp == 0 ? __uint_as_float(r[j]) : sum[c + j] + __uint_as_float(r[j]);
+          }
+        } else {
+          // frame-major tile: accumulator column = t * 2B + bin_in_tile * 2 + {re, im}.  This warp takes HALF THE BINS of every
+          // frame (B columns of each of the TFM frame groups), so that a thread ends up with all frames of its bins, i.e.
+          // with a contiguous run of the final [bin][t] layout: sum[t * B + i] <- column t * 2B + half * B + i
+          constexpr int B = TFM > 0 ? NC / (2 * TFM) : 16;
+          static_assert(TFM == 0 || B % 8 == 0, "half a frame group must be whole 8-column TMEM loads");
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TMAXN + (uint32_t)(half * B);
+#pragma unroll
+          for (int t = 0; t < (TFM > 0 ? TFM : 1); ++t) {
+#pragma unroll
+            for (int c = 0; c + 16 <= B; c += 16) {
+              uint32_t r[16];
+              tmem_ld16(taddr + t * 2 * B + c, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                sum[t * B + c + j] = sp == 0 ? __uint_as_float(r[j]) : sum[t * B + c + j] + __uint_as_float(r[j]);
+            }
+            if (B % 16) {
+              constexpr int c = B - 8;
+              uint32_t r[8];
+              tmem_ld8(taddr + t * 2 * B + c, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sum[t * B + c + j] = sp == 0 ? __uint_as_float(r[j]) : sum[t * B + c + j] + __uint_as_float(r[j]);
+            }
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -319,10 +400,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         for (int c = 0; c < H; ++c) sum[c] *= prm.out_scale;
       }
       if (kComplex) {
+        if (TFM == 0) {
 #pragma unroll
-        for (int c = 0; c < H; c += 4)
-          if (n0 + c < prm.n_out)
-            *reinterpret_cast<float4*>(prm.cplx + row * prm.n_out + n0 + c) = make_float4(sum[c], sum[c + 1], sum[c + 2], sum[c + 3]);
+          for (int c = 0; c < H; c += 4)
+            if (n0 + c < prm.n_out)
+              *reinterpret_cast<float4*>(prm.cplx + row * prm.n_out + n0 + c) = make_float4(sum[c], sum[c + 1], sum[c + 2], sum[c + 3]);
+        } else {
+          constexpr int B = TFM > 0 ? NC / (2 * TFM) : 16;                 // raw values stay in the GEMM's column order
+          float* dst = prm.cplx + row * prm.n_out + chunk * NC + half * B;
+#pragma unroll
+          for (int t = 0; t < (TFM > 0 ? TFM : 1); ++t)
+#pragma unroll
+            for (int c = 0; c < B; c += 4)
+              *reinterpret_cast<float4*>(dst + t * 2 * B + c) = make_float4(sum[t * B + c], sum[t * B + c + 1], sum[t * B + c + 2], sum[t * B + c + 3]);
+        }
       } else {
         float rmax = 0.f;
         if (TFM == 0) {
@@ -337,28 +428,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             }
           }
         } else {
-          // frame-major tile: accumulator column j = t * 2B + bin_in_tile * 2 + {re, im}  ->  final column (bin, t)
-          constexpr int B = TFM > 0 ? NC / (2 * TFM) : 1;
-          float* dst = prm.mag2 + row * n_mag + chunk * B * TFM;
+          // frame-major tile: this thread holds all TFM frames of B/2 bins (see the loads above) = a contiguous run of
+          // (B/2) * TFM values of the final [bin][t] layout, stored as 16-byte vectors
+          constexpr int B = TFM > 0 ? NC / (2 * TFM) : 16;
+          constexpr int NV = (B / 2) * (TFM > 0 ? TFM : 1);
+          static_assert(TFM == 0 || NV % 4 == 0, "a thread's run of outputs must be whole float4s");
+          float* dst = prm.mag2 + row * n_mag + (chunk * B + half * (B / 2)) * TFM;
 #pragma unroll
-          for (int c = 0; c < H; c += 2) {
-            const int j = half * H + c;
-            const int t = j / (2 * B), bl = (j - t * 2 * B) >> 1;
-            const float m = sum[c] * sum[c] + sum[c + 1] * sum[c + 1];
-            rmax = fmaxf(rmax, m);
-            dst[bl * TFM + t] = m;
+          for (int k = 0; k < NV; k += 4) {
+            float m[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int bl = (k + j) / (TFM > 0 ? TFM : 1), t = (k + j) - bl * (TFM > 0 ? TFM : 1);
+              const float re = sum[t * B + 2 * bl], im = sum[t * B + 2 * bl + 1];
+              m[j] = re * re + im * im;
+            }
+            rmax = fmaxf(fmaxf(rmax, fmaxf(m[0], m[1])), fmaxf(m[2], m[3]));
+            *reinterpret_cast<float4*>(dst + k) = make_float4(m[0], m[1], m[2], m[3]);
           }
         }
         atomicMax(reinterpret_cast<int*>(prm.rowmax + row), __float_as_int(rmax));
-        // ---- fused dB finish (cqt.py:56-58; GTC_OPT_FUSE_FINISH, default on).  The reference level of a segment is its
-        //      maximum over ALL its outputs, i.e. over the n_chunks N tiles of this 128-row block, which different CTAs
+        // ---- optional fused dB finish (cqt.py:56-58; GTC_OPT_FUSE_FINISH, OFF by default).  The reference level of a segment
+        //      is its maximum over ALL its outputs, i.e. over the n_chunks N tiles of this 128-row block, which different CTAs
         //      compute.  Every tile publishes its |C|^2 and row maxima (fence), then bumps the block's counter; the CTA
         //      that brings it to n_chunks owns the finished block and converts it while its MMA warp runs ahead into
         //      the next tile (two TMEM stages = two K splits of slack).  Nobody waits for anybody, so co-scheduling of
         //      the CTAs is not assumed.  |C|^2 is already in the final [bin][t] order (OpLayout), so the conversion is a
-        //      straight 16-byte read of the L2-resident block with 16 loads in flight per thread: ~8 us per block.
-        //      (The first version re-read |C|^2 through a [t][bin] -> [bin][t] transposing gather, one L2 round trip per
-        //      row: 60 us per block, slower than the separate finish kernel -- profiles/r01k_fused_finish.md.)
+        //      straight 16-byte read of the L2-resident block.
+        //      Measured on B200, same box (profiles/r02e_gemm_finish_ab.md): GEMM + separate finish 0.437 ms per
+        //      28 200-row chunk, fused 0.77 ms.  Two reasons, both structural: (1) the block's re-read queues behind the
+        //      TMA operand stream that saturates this SM's L2 port (~40 us per block instead of the ~16 us of slack), and
+        //      (2) the CTA that arrives last at a block is the one that is already behind, converting puts it further
+        //      behind, so the SAME CTA converts in every wave and the kernel ends when it does (+6 conversions, not +1.5).
+        //      A 4-CTA cluster exchanging row maxima through DSMEM would avoid the re-read but strands 16 of 148 SMs
+        //      (cluster size 4 packs 132); the stand-alone pass costs 19.5 us with nothing else in flight.
         if (prm.fin.out_db != nullptr) {
           const FinishArgs& f = prm.fin;
           __threadfence();
@@ -366,77 +469,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           if (warp == 2 && lane == 0) s_block_done = atomicAdd(f.tile_done + m_tile, 1) == prm.n_chunks - 1;
           asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
           if (s_block_done) {
-            __threadfence();
-            const int n_mag_f = f.n_bins * f.n_frames;
-            // clip of the warp's first row (rows of clip c start at seg_off[c] + c*(P-1)); later rows only step forward
-            int c = 0;
-            int64_t row_hi = 0, seg_hi = 0;                          // clip c owns rows < row_hi, segments < seg_hi
-            {
-              const int64_t r0 = m_tile * TBM + (warp - 2);
-              int lo = 0, hi = f.n_clips;
-              while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (__ldg(f.seg_off + mid) + (int64_t)mid * (f.parts - 1) <= r0) lo = mid; else hi = mid;
-              }
-              c = lo;
-              seg_hi = __ldg(f.seg_off + c + 1);
-              row_hi = seg_hi + (int64_t)(c + 1) * (f.parts - 1);
-            }
-            constexpr int RG = 2;                                    // rows in flight per warp (x 4 vectors per lane)
-            for (int i0 = warp - 2; i0 < TBM; i0 += TC_EPI_WARPS * RG) {
-              int64_t seg[RG];
-#pragma unroll
-              for (int k = 0; k < RG; ++k) {
-                const int64_t r = m_tile * TBM + i0 + TC_EPI_WARPS * k;
-                seg[k] = -1;
-                if (r < f.n_rows) {
-                  while (r >= row_hi && c + 1 < f.n_clips) {
-                    ++c;
-                    seg_hi = __ldg(f.seg_off + c + 1);
-                    row_hi = seg_hi + (int64_t)(c + 1) * (f.parts - 1);
-                  }
-                  const int64_t g = r - (int64_t)c * (f.parts - 1);  // the clip's last P-1 rows start no segment
-                  if (g < seg_hi) seg[k] = g;
-                }
-              }
-              if ((n_mag_f & 3) == 0) {
-                const int nv = n_mag_f >> 2;
-                for (int ob = 0; ob < nv; ob += 128) {
-                  float4 v[RG][4];
-                  float ref[RG];
-#pragma unroll
-                  for (int k = 0; k < RG; ++k) {
-                    const int64_t r = m_tile * TBM + i0 + TC_EPI_WARPS * k;
-                    ref[k] = seg[k] >= 0 ? __ldcg(prm.rowmax + r) : 0.f;
-                    const float4* s4 = reinterpret_cast<const float4*>(prm.mag2 + r * n_mag_f);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                      const int o = ob + lane + 32 * u;
-                      v[k][u] = (seg[k] >= 0 && o < nv) ? __ldcg(s4 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                  }
-#pragma unroll
-                  for (int k = 0; k < RG; ++k) {
-                    if (seg[k] < 0) continue;
-                    const DbScale scale(ref[k], f.power, f.amin, f.top_db, f.cut_db, f.floor_db);
-                    float4* d4 = reinterpret_cast<float4*>(f.out_db + seg[k] * n_mag_f);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                      const int o = ob + lane + 32 * u;
-                      if (o < nv) d4[o] = make_float4(scale(v[k][u].x), scale(v[k][u].y), scale(v[k][u].z), scale(v[k][u].w));
-                    }
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int k = 0; k < RG; ++k) {
-                  const int64_t r = m_tile * TBM + i0 + TC_EPI_WARPS * k;
-                  if (seg[k] >= 0)
-                    finish_row_db(prm.mag2 + r * n_mag_f, __ldcg(prm.rowmax + r), f.out_db + seg[k] * n_mag_f, lane, f.n_bins,
-                                  f.n_frames, f.power, f.amin, f.top_db, f.cut_db, f.floor_db);
-                }
-              }
-            }
+            fused_finish_block(prm, m_tile, warp, lane);
             if (warp == 2 && lane == 0) f.tile_done[m_tile] = 0;     // ready for the next contraction over this workspace
           }
         }

@@ -254,9 +254,9 @@ sfinish_kernel(float* __restrict__ io, const float* __restrict__ segmax, int64_t
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = i / per_seg;
     const float ref = s_of(__ldg(segmax + s));
-    const float ref_db = 10.f * log10f(fmaxf(amin2, ref * ref));
+    const float ref_db = ten_log10(fmaxf(amin2, ref * ref));
     const float v = s_of(io[i]);
-    float db = 10.f * log10f(fmaxf(amin2, v * v)) - ref_db;
+    float db = ten_log10(fmaxf(amin2, v * v)) - ref_db;
     db = fmaxf(db, 0.f - top_db);
     if (db < cut_db) db = floor_db;
     io[i] = db;

@@ -61,6 +61,7 @@ __device__ __forceinline__ int find_clip(const int64_t* __restrict__ off, int n,
 struct FinishArgs {
   float* out_db;             // [n_seg][n_bins][n_frames]; null = do not fuse (the caller runs finish_db_kernel)
   const int64_t* seg_off;    // [n_clips + 1]
+  const int* seg_of_row;     // [n_rows_pad] segment started by each operand row, -1 for a clip's last P-1 rows and padding (frame_kernel)
   int* tile_done;            // [n_rows_pad / 128] counters, zero before the launch (frame_kernel) and after it
   int n_clips, parts, n_bins, n_frames;
   int64_t n_rows, n_seg;
@@ -75,6 +76,19 @@ __device__ __forceinline__ float mag_power(float m2, float power) {
   return powf(m2, 0.5f * power);
 }
 
+// 10 * log10(x) through MUFU.LG2 (__log2f: abs. error 2^-22 of the logarithm, i.e. < 2e-6 dB against the 0.01 dB gate).
+// The dB passes were bound by the ~30-instruction log10f subroutine: finish_db_kernel 44 -> 19 us per 28 200-row chunk on
+// B200 (same box, profiles/r02e_gemm_finish_ab.md).  -DGTC_EXACT_LOG restores log10f.
+__device__ __forceinline__ float ten_log10(float x) {
+#ifdef GTC_EXACT_LOG
+  return 10.f * log10f(x);
+#else
+  // __fmul_rn: the product must be rounded on its own -- contracted into `fma(c, log2 x, -ref_db)` the segment's peak element
+  // would come out as the rounding error of c * log2(ref) instead of exactly 0 dB
+  return __fmul_rn(3.010299956639812f, __log2f(x));
+#endif
+}
+
 // dB value of one element given the segment's reference (both as |C|^2)
 struct DbScale {
   float power, amin2, ref_db, lo_clamp, cut_db, floor_db;
@@ -82,12 +96,12 @@ struct DbScale {
       : power(power_), amin2(amin * amin), cut_db(cut_db_), floor_db(floor_db_) {
     // S = |C|^power ; amplitude_to_db squares it again: 10*log10(max(amin^2, S^2)) - 10*log10(max(amin^2, ref^2))
     const float ref = mag_power(m2max, power);
-    ref_db = 10.f * log10f(fmaxf(amin2, ref * ref));
+    ref_db = ten_log10(fmaxf(amin2, ref * ref));
     lo_clamp = 0.f - top_db;         // log_spec.max() is the peak element's own value -> exactly 0 dB
   }
   __device__ __forceinline__ float operator()(float m2) const {
     const float s = mag_power(m2, power);
-    float db = 10.f * log10f(fmaxf(amin2, s * s)) - ref_db;
+    float db = ten_log10(fmaxf(amin2, s * s)) - ref_db;
     db = fmaxf(db, lo_clamp);
     return db < cut_db ? floor_db : db;
   }
@@ -172,7 +186,7 @@ struct PlanImpl {
 // launchers (each enqueues on `st`, returns a GTC_* code); xhi/xlo element type follows PlanImpl::elem_bytes
 int launch_frame(const PlanImpl& p, const void* d_audio, int pcm16, const int64_t* d_clip_off, const int64_t* d_seg_off,
                  int n_clips, int64_t n_rows, int64_t n_rows_alloc, void* d_xhi, void* d_xlo, float* d_rowmax,
-                 int* d_tile_done, cudaStream_t st);
+                 int* d_tile_done, int* d_seg_of_row, cudaStream_t st);
 inline OpLayout op_layout(const PlanImpl& p) { return OpLayout{p.nc, p.bins_per_tile, p.n_bins, p.n_frames}; }
 int launch_gemm_simt(const PlanImpl& p, const float* d_xhi, const float* d_xlo, int64_t n_rows_pad,
                      float* d_mag2, float* d_cplx, float* d_rowmax, cudaStream_t st);
@@ -182,8 +196,8 @@ int tc_plan_init(PlanImpl& p);
 int tc_pick_plain_width(int n_out);                       // tile width of the plain row order
 bool tc_has_frame_major_kernel(int nc, int n_frames);     // is gemm_tc_kernel instantiated for this frame-major tile?
 void tc_plan_free(PlanImpl& p);
-int launch_finish_db(const PlanImpl& p, const float* d_mag2, const float* d_rowmax, const int64_t* d_seg_off,
-                     int n_clips, int64_t n_seg, float* d_out_db, float power, float amin, float top_db, float cut_db,
+int launch_finish_db(const PlanImpl& p, const float* d_mag2, const float* d_rowmax, const int* d_seg_of_row,
+                     int64_t n_rows, float* d_out_db, float power, float amin, float top_db, float cut_db,
                      float floor_db, cudaStream_t st);
 int launch_finish_complex(const PlanImpl& p, const float* d_cplx, const int64_t* d_seg_off, int n_clips, int64_t n_seg,
                           float* d_out, cudaStream_t st);

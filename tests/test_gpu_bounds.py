@@ -40,9 +40,9 @@ def test_outputs_and_workspace_stay_inside_their_buffers(lib, recipe):
         n_seg = int(so[-1])
         co_t, so_t = torch.from_numpy(co).to(dev), torch.from_numpy(so).to(dev)
         ws = g((plan.workspace_bytes(n_seg, len(lens)),), torch.uint8)                # exactly what the library asks for
-        db = plan.segments_db(audio, co_t, so_t, n_seg, out=g((n_seg, 96, 5), torch.float32), workspace=ws)
+        db = plan.segments_db(audio, co_t, so_t, n_seg, out=g((n_seg, 96, 5), torch.float32), workspace=ws)   # fused dB finish (default)
         if engine != _lib.GTC_GEMM_SIMT_FP32:
-            plan.configure(_lib.GTC_OPT_FUSE_FINISH, 1)
+            plan.configure(_lib.GTC_OPT_FUSE_FINISH, 0)                                # separate finish_db_kernel
             plan.segments_db(audio, co_t, so_t, n_seg, out=g((n_seg, 96, 5), torch.float32), workspace=ws)
         torch.cuda.synchronize()
         plan.close()
