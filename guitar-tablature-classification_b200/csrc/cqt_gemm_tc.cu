@@ -56,6 +56,7 @@ struct TcParams {
   float* cplx;           // [rows][n_out]   or null
   float* rowmax;         // [rows]
   FinishArgs fin;        // fin.out_db != null: the CTA that completes the last N tile of a 128-row block also does its dB finish
+  SlotArgs slots;        // SLOT > 0 kernels: slotted rows of the structured CQT
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -85,6 +86,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -210,7 +216,8 @@ __device__ __forceinline__ void fused_finish_block(const TcParams& prm, int64_t 
 // (r01 experiment: -DTC_MAXNREG=152 lets one 224-thread x 72-register patch CTA (patches.cu) fit beside this one; co-running
 // the two kernels measured SLOWER than back to back -- both live on L2 bandwidth -- profiles/r01j_coresident.md.)
 // TFM > 0: frame-major tiles (OpLayout, gtc_common.cuh) of a TFM-frame recipe: NC = 2 * TFM * bins_per_tile; 0: plain rows.
-template <int NC, bool kComplex, bool kHalf, int TFM>
+// SLOT > 0: the M operand is slotted (SlotArgs, gtc_common.cuh): 1 = decimator epilogue, 2 = response epilogue.
+template <int NC, bool kComplex, bool kHalf, int TFM, int SLOT = 0>
 __global__ void __maxnreg__(TC_MAXNREG)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo,
@@ -218,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   constexpr int H = NC / 2;                  // columns per epilogue warp
   constexpr int EPK = TKB_BYTES / (kHalf ? 2 : 4);   // operand elements per k-block
   static_assert(NC % 16 == 0 && NC <= TMAXN && H % 8 == 0, "unsupported tile width");
-  static_assert(TFM == 0 || NC % (2 * TFM) == 0, "a frame-major tile holds whole bins x TFM frames");
+  static_assert(TFM == 0 || NC % (TFM > 0 ? 2 * TFM : 1) == 0, "a frame-major tile holds whole bins x TFM frames");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bars[2 * TSTAGES + 4];
   __shared__ uint32_t s_tmem_slot;
@@ -276,8 +283,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           mbar_expect_tx(bar_full(stage), stage_tx);
           const int p = kb / prm.kb_per_part;
           const int kx = (kb - p * prm.kb_per_part) * EPK;
-          tma_load_2d(st_xhi(stage), &tm_xhi, bar_full(stage), kx, row0 + p);
-          tma_load_2d(st_xlo(stage), &tm_xlo, bar_full(stage), kx, row0 + p);
+          if (SLOT == 0) {
+            tma_load_2d(st_xhi(stage), &tm_xhi, bar_full(stage), kx, row0 + p);
+            tma_load_2d(st_xlo(stage), &tm_xlo, bar_full(stage), kx, row0 + p);
+          } else {                                           // 16 segments x 8 consecutive rows (windows) of each
+            const int sg = (int)(m_tile / prm.slots.jgroups), jg = (int)(m_tile - (int64_t)sg * prm.slots.jgroups);
+            tma_load_3d(st_xhi(stage), &tm_xhi, bar_full(stage), kx, 8 * jg, 16 * sg);
+            tma_load_3d(st_xlo(stage), &tm_xlo, bar_full(stage), kx, 8 * jg, 16 * sg);
+          }
           tma_load_2d(st_ohi(stage), &tm_ohi, bar_full(stage), kb * EPK, n0);
 #ifndef TC_EXP_SKIP_OLO
           tma_load_2d(st_olo(stage), &tm_olo, bar_full(stage), kb * EPK, n0);
@@ -399,7 +412,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 #pragma unroll
         for (int c = 0; c < H; ++c) sum[c] *= prm.out_scale;
       }
-      if (kComplex) {
+      if (SLOT > 0) {
+        // ---- structured CQT: tile row rho = 8 * (segment within the group of 16) + (row within the group of 8)
+        const SlotArgs& sl = prm.slots;
+        const int rho = q * 32 + lane;
+        const int sg = (int)(m_tile / sl.jgroups), jg = (int)(m_tile - (int64_t)sg * sl.jgroups);
+        const int64_t slot = 16 * (int64_t)sg + (rho >> 3);
+        const int j = 8 * jg + (rho & 7);
+        const bool live = slot < sl.n_slots;
+        const int len0 = live ? __ldg(sl.seg_len + slot) : 0;
+        if (SLOT == 1) {
+          // decimator: row j holds outputs k = j * NC + n of the next octave; beyond the octave's length -> zeros (librosa
+          // fixes the length to ceil(n / 2), and the next stage must see a zero-extended signal)
+          const int valid = halved_len(len0, sl.stage_out);
+          if (live) {
+            __half* hi = sl.out_hi + sl.out_base + slot * sl.out_stride + (int64_t)j * NC + half * H;
+            __half* lo = sl.out_lo + sl.out_base + slot * sl.out_stride + (int64_t)j * NC + half * H;
+            const int k0 = j * NC + half * H;
+#pragma unroll
+            for (int c = 0; c < H; c += 8) {
+              __align__(16) __half h8[8], l8[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const float v = (k0 + c + u < valid) ? sum[c + u] * sl.plane_scale : 0.f;
+                h8[u] = __float2half_rn(v);
+                l8[u] = __float2half_rn(v - __half2float(h8[u]));
+              }
+              *reinterpret_cast<uint4*>(hi + c) = *reinterpret_cast<const uint4*>(h8);
+              *reinterpret_cast<uint4*>(lo + c) = *reinterpret_cast<const uint4*>(l8);
+            }
+          }
+        } else {
+          // response: row j = frame t of the segment, columns = (bin, {re, im}) of the octave's filters
+          const int t = j;
+          const bool valid = live && t < cqt_frames_of(len0, sl.hop0, sl.n_oct);
+          float mx = 0.f;
+#pragma unroll
+          for (int c = 0; c < H; c += 2) {
+            const int b = (half * H + c) >> 1;
+            const float m = valid ? sum[c] * sum[c] + sum[c + 1] * sum[c + 1] : 0.f;
+            if (live && t < sl.t_max && b < sl.bin_cnt) {
+              sl.out[(slot * sl.n_bins + sl.bin_lo + b) * sl.t_max + t] = m;
+              mx = fmaxf(mx, m);
+            }
+          }
+          // the 8 lanes of a segment's row group share one atomic
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+          if ((rho & 7) == 0 && live && mx > 0.f) atomicMax(reinterpret_cast<int*>(sl.segmax + slot), __float_as_int(mx));
+        }
+      } else if (kComplex) {
         if (TFM == 0) {
 #pragma unroll
           for (int c = 0; c < H; c += 4)
@@ -522,7 +585,7 @@ static int encode_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t 
 
 // Kernel instantiations: plain row order for a few tile widths, frame-major tiles (NC = 2 * T * bins_per_tile) for the
 // recipes in use: T = 5 (22.05 kHz, cqt.py recipe: 24 bins x 5 frames x 2 = 240) and T = 9 (44.1 kHz: 8 x 9 x 2 = 144).
-static const int kPlainWidths[] = {256, 192, 128, 64};
+static const int kPlainWidths[] = {256, 192, 128, 64, 32};
 
 int tc_pick_plain_width(int n_out) {
   for (int nc : kPlainWidths)
@@ -556,6 +619,7 @@ static int for_plan_kernels(const PlanImpl& p, int cplx, int half, F&& f) {
     case 192: return for_variant<192, 0>(cplx, half, f);
     case 128: return for_variant<128, 0>(cplx, half, f);
     case 64: return for_variant<64, 0>(cplx, half, f);
+    case 32: return for_variant<32, 0>(cplx, half, f);
     default: set_error("no tensor-core kernel for tile width %d", p.nc); return GTC_E_UNSUP;
   }
 }
@@ -609,6 +673,66 @@ int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int6
     return GTC_OK;
   });
   if (rc != GTC_OK) return rc;
+  GTC_CUDA_CHECK(cudaGetLastError());
+  return GTC_OK;
+}
+
+// ---- structured CQT: slotted rows (SlotArgs).  3-D map over one fp16 plane: (sample within the window, row within the
+// segment, segment); rows overlap (row stride < window length), box = one k-block x 8 rows x 16 segments = a 128-row tile.
+static int encode_3d(CUtensorMap* tm, const void* base, uint64_t k_extent, uint64_t rows, uint64_t slots, uint64_t row_step,
+                     uint64_t slot_stride) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return GTC_E_CUDA;
+  cuuint64_t gdim[3] = {k_extent, rows, slots};
+  cuuint64_t gstr[2] = {row_step * 2, slot_stride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)(TKB_BYTES / 2), 8, 16};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  TKB_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : TKB_BYTES == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GTC_REQUIRE(r == CUDA_SUCCESS, GTC_E_CUDA, "cuTensorMapEncodeTiled (3-D, overlapping rows) failed with CUresult %d", (int)r);
+  return GTC_OK;
+}
+
+int launch_gemm_tc_slots(const PlanImpl& p, const __half* x_hi, const __half* x_lo, int64_t x_first, int64_t x_stride,
+                         int64_t row_step, int rows_per_slot, const SlotArgs& slots, cudaStream_t st) {
+  GTC_REQUIRE(p.tmap_op_hi != nullptr && p.elem_bytes == 2 && p.parts == 1, GTC_E_ARG, "slotted GEMM needs an fp16x2 plan with one part");
+  GTC_REQUIRE(p.bins_per_tile == 0 && p.n_out <= p.nc, GTC_E_ARG, "slotted GEMM: the operator must be one plain N tile");
+  GTC_REQUIRE((slots.slot_mode == 1 && p.nc == 128) || (slots.slot_mode == 2 && p.nc == 32), GTC_E_UNSUP,
+              "slotted GEMM: no kernel for mode %d with tile width %d", slots.slot_mode, p.nc);
+  GTC_REQUIRE(rows_per_slot > 0 && rows_per_slot % 8 == 0 && slots.n_slots > 0, GTC_E_ARG, "slotted GEMM: bad geometry");
+  GTC_REQUIRE(((x_first * 2) & 15) == 0 && ((row_step * 2) & 15) == 0 && ((x_stride * 2) & 15) == 0, GTC_E_ARG,
+              "slotted GEMM: windows must start on 16-byte boundaries");
+  CUtensorMap tm_xhi, tm_xlo;
+  int rc = encode_3d(&tm_xhi, x_hi + x_first, (uint64_t)p.kp, (uint64_t)rows_per_slot, (uint64_t)slots.n_slots, (uint64_t)row_step, (uint64_t)x_stride);
+  if (rc != GTC_OK) return rc;
+  rc = encode_3d(&tm_xlo, x_lo + x_first, (uint64_t)p.kp, (uint64_t)rows_per_slot, (uint64_t)slots.n_slots, (uint64_t)row_step, (uint64_t)x_stride);
+  if (rc != GTC_OK) return rc;
+  TcParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.nc = p.nc;
+  prm.kb_per_split = (p.tc_kb_per_split > 0 ? p.tc_kb_per_split : 8) * (128 / TKB_BYTES);
+  prm.n_chunks = 1;
+  prm.n_out = p.n_out;
+  prm.kb_per_part = p.kp / p.kb_elems;
+  prm.out_scale = p.out_scale;
+  prm.parts = 1;
+  prm.slots = slots;
+  prm.slots.jgroups = rows_per_slot / 8;
+  prm.m_tiles = ceil_div(slots.n_slots, 16) * prm.slots.jgroups;
+  const unsigned grid = (unsigned)(prm.m_tiles < p.sm_count ? prm.m_tiles : p.sm_count);
+  const CUtensorMap& tm_ohi = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_hi);
+  const CUtensorMap& tm_olo = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_lo);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128, false, true, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<32, false, true, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  if (slots.slot_mode == 1)
+    gemm_tc_kernel<128, false, true, 0, 1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
+  else
+    gemm_tc_kernel<32, false, true, 0, 2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;
 }

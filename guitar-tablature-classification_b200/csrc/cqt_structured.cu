@@ -15,7 +15,20 @@
 //   finish_kernel     : |C|^power -> amplitude_to_db(ref=max over the segment, amin, top_db) -> cut   (in place)
 //
 // Everything is HBM/L2-bound streaming work except the FIR (389 taps), which is shared-memory bound.
+//
+// Round 2: for dB features both contractions run on the tcgen05 engine of cqt_gemm_tc.cu (SlotArgs, gtc_common.cuh).  The
+// signals of every octave live as fp16 hi/lo planes (x * 2^8 split into two halves, 22 mantissa bits), one zero-guarded
+// slot per segment:
+//   split_kernel        audio (fp32 / int16 PCM) -> octave-0 planes
+//   decimator GEMM      rows = 128-output windows of 672 input samples (row step 256: overlapping TMA rows) x a fixed
+//                       banded Toeplitz operator [128][672] of the taps; epilogue writes the next octave's planes
+//   response GEMM       rows = frames (n_fft samples, row step hop_i) x the octave's filters [32][n_fft]; epilogue
+//                       writes |C|^2 into [seg][bin][t] and the segment maximum
+//   sfinish_kernel      in-place dB
+// The fp32 SIMT kernels below stay for complex output, the stand-alone decimator API and recipes the tensor path does not
+// take (more than 16 filters per octave, hops that leave the lowest octave's frames off 16-byte boundaries).
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include <vector>
 #include "gtc_common.cuh"
@@ -28,6 +41,10 @@ constexpr int kFramesPerCta = 32;
 
 struct SPlanImpl {
   int device, sm_count;
+  int use_tc;               // both contractions on the tensor cores (dB output)
+  int dec_left, dec_k;      // Toeplitz window: starts dec_left samples before input 2k0, dec_k samples long
+  void* dec_plan;           // gtc_plan* of the Toeplitz operator [128][dec_k]
+  void* resp_plan[kMaxOctaves];   // gtc_plan* of octave i's filters [32][n_fft]
   int n_oct, n_fft, hop, n_bins, n_filters, n_taps;
   int groups;               // float4 groups of the 2*n_filters real outputs of one octave
   int bin_lo[kMaxOctaves];  // first output bin of octave i (octave 0 = top octave)
@@ -44,21 +61,8 @@ struct OctaveBufs {
 __device__ __forceinline__ float s_load(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float s_load(const int16_t* p) { return (float)__ldg(p) * (1.f / 32768.f); }
 
-__device__ __forceinline__ int halved(int n, int times) {
-  for (int i = 0; i < times; ++i) n = (n + 1) >> 1;
-  return n;
-}
-
-// frames librosa keeps (__trim_stack): min over octaves of 1 + len_i // hop_i
-__device__ __host__ __forceinline__ int frames_of(int len, int hop, int n_oct) {
-  int t = 0x7fffffff;
-  for (int i = 0; i < n_oct; ++i) {
-    const int f = 1 + len / hop;
-    t = f < t ? f : t;
-    if ((hop & 1) == 0) { hop >>= 1; len = (len + 1) >> 1; }
-  }
-  return t;
-}
+__device__ __forceinline__ int halved(int n, int times) { return halved_len(n, times); }
+__device__ __host__ __forceinline__ int frames_of(int len, int hop, int n_oct) { return cqt_frames_of(len, hop, n_oct); }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // 2:1 decimator.  blockIdx.x = segment * tiles + tile.
@@ -263,6 +267,80 @@ sfinish_kernel(float* __restrict__ io, const float* __restrict__ segmax, int64_t
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// tensor-core path: plane geometry, the split kernel and the launch sequence
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kPlaneFront = 512;          // zero samples in front of segment 0 (windows start before their segment)
+constexpr float kPlaneScale = 256.f;      // == the fp16x2 engine's x_scale (cqt_api.cu)
+
+struct TcGeom {
+  int64_t S[kMaxOctaves];                 // samples per segment slot of octave i (multiple of 1024, >= len_i + guard)
+  int64_t plane_elems[kMaxOctaves];       // halves per plane
+  size_t off_hi[kMaxOctaves], off_lo[kMaxOctaves];
+  int t_pad;                              // frames per segment, padded to 8
+};
+
+static void tc_geometry(const SPlanImpl& p, int64_t n_seg, int64_t max_len, TcGeom& g) {
+  const int t_max = frames_of((int)max_len, p.hop, p.n_oct);
+  g.t_pad = (int)round_up(t_max, 8);
+  int64_t len = max_len;
+  const int64_t guard = p.dec_left + 8 > p.n_fft / 2 ? p.dec_left + 8 : p.n_fft / 2;
+  for (int i = 0; i < p.n_oct; ++i) {
+    g.S[i] = round_up(len + guard, 1024);
+    len = (len + 1) / 2;
+  }
+  for (int i = 0; i < p.n_oct; ++i) {
+    // furthest sample any window of the last segment touches, past that segment's slot
+    int64_t reach = (int64_t)g.t_pad * (p.hop >> i) + p.n_fft;                       // response frames
+    if (i + 1 < p.n_oct) reach = reach > 2 * g.S[i + 1] + p.dec_k ? reach : 2 * g.S[i + 1] + p.dec_k;   // decimator windows
+    const int64_t tail = reach > g.S[i] ? reach - g.S[i] : 0;
+    g.plane_elems[i] = round_up(kPlaneFront + n_seg * g.S[i] + tail + 64, 512);
+  }
+}
+
+// The zero front and the tail of every plane (everything between them is written by the split kernel / the decimator
+// epilogues).  The tail matters: a window of the last segment reaches past its slot, and although the operator is zero
+// there, 0 x (uninitialised NaN bit pattern) would poison the row.
+struct PadList {
+  __half* plane[2 * kMaxOctaves];
+  int64_t tail_at[2 * kMaxOctaves], tail_len[2 * kMaxOctaves];
+  int n;
+};
+__global__ void __launch_bounds__(256) pad_zero_kernel(const PadList pl) {
+  for (int i = blockIdx.y; i < pl.n; i += gridDim.y) {
+    __half* p = pl.plane[i];
+    const int64_t total = kPlaneFront + pl.tail_len[i];
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x)
+      p[k < kPlaneFront ? k : pl.tail_at[i] + (k - kPlaneFront)] = __float2half(0.f);
+  }
+}
+
+// octave-0 planes: every sample of every slot is written (zeros beyond the segment), 8 samples per thread
+template <typename In>
+__global__ void __launch_bounds__(256)
+split_kernel(const In* __restrict__ audio, const int64_t* __restrict__ seg_start, const int32_t* __restrict__ seg_valid,
+             const int32_t* __restrict__ seg_len, int64_t n_seg, int64_t S, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int64_t per_seg = S >> 3;
+  const int64_t total = n_seg * per_seg;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / per_seg;
+    const int64_t k0 = (i - s * per_seg) << 3;
+    const int readable = min(__ldg(seg_len + s), __ldg(seg_valid + s));
+    const In* x = audio + __ldg(seg_start + s);
+    __align__(16) __half h8[8], l8[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float v = (k0 + u < readable) ? s_load(x + k0 + u) * kPlaneScale : 0.f;
+      h8[u] = __float2half_rn(v);
+      l8[u] = __float2half_rn(v - __half2float(h8[u]));
+    }
+    const int64_t at = kPlaneFront + s * S + k0;
+    *reinterpret_cast<uint4*>(hi + at) = *reinterpret_cast<const uint4*>(h8);
+    *reinterpret_cast<uint4*>(lo + at) = *reinterpret_cast<const uint4*>(l8);
+  }
+}
+
 static inline size_t dec_smem_bytes(int n_taps) {
   const int c = (n_taps - 1) / 2, nt = (c + 4) & ~3;
   return (size_t)(2 * nt + 2 * (kDecTile + nt + 4)) * sizeof(float);
@@ -270,7 +348,8 @@ static inline size_t dec_smem_bytes(int n_taps) {
 
 struct SWorkspace {
   OctaveBufs bufs;
-  size_t off_segmax, total;
+  TcGeom tc;
+  size_t off_segmax, total, total_tc;
 };
 
 static SWorkspace s_layout(const SPlanImpl& p, int64_t n_seg, int64_t max_len) {
@@ -279,14 +358,87 @@ static SWorkspace s_layout(const SPlanImpl& p, int64_t n_seg, int64_t max_len) {
   size_t o = 0;
   auto take = [&](size_t b) { size_t at = o; o += (b + 1023) & ~(size_t)1023; return at; };
   w.off_segmax = take((size_t)(n_seg > 0 ? n_seg : 1) * sizeof(float));
+  if (p.use_tc && n_seg > 0 && max_len > 0) {             // tensor path: hi/lo planes of every octave, after the maxima
+    size_t o_tc = o;
+    auto take_tc = [&](size_t b) { size_t at = o_tc; o_tc += (b + 1023) & ~(size_t)1023; return at; };
+    tc_geometry(p, n_seg, max_len, w.tc);
+    for (int i = 0; i < p.n_oct; ++i) {
+      w.tc.off_hi[i] = take_tc((size_t)w.tc.plane_elems[i] * sizeof(__half));
+      w.tc.off_lo[i] = take_tc((size_t)w.tc.plane_elems[i] * sizeof(__half));
+    }
+    w.total_tc = o_tc;
+  }
   int64_t len = max_len;
   for (int i = 1; i < p.n_oct; ++i) {
     len = (len + 1) / 2;
     w.bufs.stride[i] = round_up(len, 4);
     w.bufs.off[i] = (int64_t)(take((size_t)n_seg * w.bufs.stride[i] * sizeof(float)) / sizeof(float));
   }
-  w.total = o;
+  w.total = o > w.total_tc ? o : w.total_tc;              // one workspace serves both paths (complex output is SIMT only)
   return w;
+}
+
+// dB features with both contractions on the tensor cores
+template <typename In>
+static int run_structured_tc(const SPlanImpl& p, const In* d_audio, const int64_t* d_seg_start, const int32_t* d_seg_valid,
+                             const int32_t* d_seg_len, int64_t n_seg, int64_t max_len, float* d_out, char* ws, const SWorkspace& w,
+                             float power, float amin, float top_db, float cut_db, float floor_db, cudaStream_t st) {
+  const TcGeom& g = w.tc;
+  float* segmax = reinterpret_cast<float*>(ws + w.off_segmax);
+  const int t_max = frames_of((int)max_len, p.hop, p.n_oct);
+  GTC_CUDA_CHECK(cudaMemsetAsync(segmax, 0, (size_t)n_seg * sizeof(float), st));
+  auto hi = [&](int i) { return reinterpret_cast<__half*>(ws + g.off_hi[i]); };
+  auto lo = [&](int i) { return reinterpret_cast<__half*>(ws + g.off_lo[i]); };
+  {
+    PadList pl;
+    pl.n = 2 * p.n_oct;
+    for (int i = 0; i < p.n_oct; ++i)
+      for (int h = 0; h < 2; ++h) {
+        pl.plane[2 * i + h] = h ? lo(i) : hi(i);
+        pl.tail_at[2 * i + h] = kPlaneFront + n_seg * g.S[i];
+        pl.tail_len[2 * i + h] = g.plane_elems[i] - (kPlaneFront + n_seg * g.S[i]);
+      }
+    pad_zero_kernel<<<dim3(8, (unsigned)pl.n), 256, 0, st>>>(pl);
+    GTC_CUDA_CHECK(cudaGetLastError());
+  }
+  {
+    int64_t blocks = ceil_div(n_seg * (g.S[0] >> 3), 256);
+    const int64_t cap = (int64_t)p.sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    split_kernel<In><<<(unsigned)blocks, 256, 0, st>>>(d_audio, d_seg_start, d_seg_valid, d_seg_len, n_seg, g.S[0], hi(0), lo(0));
+    GTC_CUDA_CHECK(cudaGetLastError());
+  }
+  SlotArgs sl;
+  memset(&sl, 0, sizeof(sl));
+  sl.n_slots = n_seg;
+  sl.seg_len = d_seg_len;
+  sl.plane_scale = kPlaneScale;
+  const PlanImpl& dec = *reinterpret_cast<const PlanImpl*>(p.dec_plan);
+  for (int i = 0; i + 1 < p.n_oct; ++i) {                 // octave i+1 = 2:1 decimation of octave i
+    sl.slot_mode = 1;
+    sl.out_hi = hi(i + 1); sl.out_lo = lo(i + 1);
+    sl.out_stride = g.S[i + 1]; sl.out_base = kPlaneFront;
+    sl.stage_out = i + 1;
+    int rc = launch_gemm_tc_slots(dec, hi(i), lo(i), kPlaneFront - p.dec_left, g.S[i], 256, (int)(g.S[i + 1] / 128), sl, st);
+    if (rc != GTC_OK) return rc;
+  }
+  sl.slot_mode = 2;
+  sl.out = d_out; sl.segmax = segmax;
+  sl.n_bins = p.n_bins; sl.t_max = t_max; sl.hop0 = p.hop; sl.n_oct = p.n_oct;
+  for (int i = 0; i < p.n_oct; ++i) {
+    sl.bin_lo = p.bin_lo[i]; sl.bin_cnt = p.bin_cnt[i];
+    const PlanImpl& rp = *reinterpret_cast<const PlanImpl*>(p.resp_plan[i]);
+    int rc = launch_gemm_tc_slots(rp, hi(i), lo(i), kPlaneFront - p.n_fft / 2, g.S[i], p.hop >> i, g.t_pad, sl, st);
+    if (rc != GTC_OK) return rc;
+  }
+  const int per_seg = p.n_bins * t_max;
+  int64_t fblocks = ceil_div(n_seg * per_seg, 256 * 4);
+  const int64_t cap = (int64_t)p.sm_count * 16;
+  if (fblocks > cap) fblocks = cap;
+  if (fblocks < 1) fblocks = 1;
+  sfinish_kernel<<<(unsigned)fblocks, 256, 0, st>>>(d_out, segmax, n_seg, per_seg, power, amin, top_db, cut_db, floor_db);
+  GTC_CUDA_CHECK(cudaGetLastError());
+  return GTC_OK;
 }
 
 template <typename In>
@@ -416,6 +568,44 @@ extern "C" int gtc_scqt_plan_create(gtc_splan** out, int device, int n_octaves, 
     delete plan;
     return GTC_E_CUDA;
   }
+  // ---- tensor-core path (dB output): the decimator as a banded Toeplitz operator, the octave filters as [32][n_fft]
+  //      operators, each an fp16x2 plan of the segment-operator engine (cqt_api.cu).  Window geometry of the decimator:
+  //      row j of a segment produces outputs k = 128 j + n, n < 128, from the inputs 256 j - left .. 256 j - left + K - 1,
+  //      left = c rounded up to 8 (16-byte window starts), out[k] = sum_m h[m] x[2k + c - m]  =>  Op[n][i] = h[2n + c + left - i].
+  p.use_tc = 0;
+  bool eligible = filters_per_octave <= 16 && n_fft % 32 == 0 && getenv("GTC_SCQT_SIMT") == nullptr;
+  for (int i = 0; i < n_octaves; ++i) eligible = eligible && ((hop_length >> i) % 8 == 0);
+  if (eligible) {
+    const int c = (n_taps - 1) / 2;
+    p.dec_left = (int)round_up(c, 8);
+    p.dec_k = (int)round_up(p.dec_left + 254 + c + 1, 32);
+    eligible = p.dec_left + 8 <= kPlaneFront && n_fft / 2 <= kPlaneFront;
+  }
+  if (eligible) {
+    std::vector<float> op((size_t)128 * p.dec_k, 0.f);
+    const int c = (n_taps - 1) / 2;
+    for (int n = 0; n < 128; ++n)
+      for (int i = 0; i < p.dec_k; ++i) {
+        const int m = 2 * n + c + p.dec_left - i;
+        if (m >= 0 && m < n_taps) op[(size_t)n * p.dec_k + i] = h_taps[m];
+      }
+    gtc_plan* sub = nullptr;
+    int rc = gtc_cqt_plan_create(&sub, device, p.dec_k, p.dec_k, 64, 1, op.data(), GTC_GEMM_TCGEN05_FP16X2);
+    p.dec_plan = sub;
+    for (int i = 0; i < n_octaves && rc == GTC_OK; ++i) {
+      std::vector<float> f((size_t)32 * n_fft, 0.f);
+      for (int r = 0; r < n_real && r < 32; ++r)
+        memcpy(&f[(size_t)r * n_fft], &h_filters[((size_t)i * n_real + r) * n_fft], (size_t)n_fft * sizeof(float));
+      sub = nullptr;
+      rc = gtc_cqt_plan_create(&sub, device, n_fft, n_fft, 16, 1, f.data(), GTC_GEMM_TCGEN05_FP16X2);
+      p.resp_plan[i] = sub;
+    }
+    if (rc != GTC_OK) {
+      gtc_scqt_plan_destroy(plan);
+      return rc;
+    }
+    p.use_tc = 1;
+  }
   *out = plan;
   return GTC_OK;
 }
@@ -424,6 +614,9 @@ extern "C" int gtc_scqt_plan_destroy(gtc_splan* plan) {
   if (!plan) return GTC_OK;
   if (plan->impl.d_filters) cudaFree(plan->impl.d_filters);
   if (plan->impl.d_taps) cudaFree(plan->impl.d_taps);
+  if (plan->impl.dec_plan) gtc_cqt_plan_destroy(reinterpret_cast<gtc_plan*>(plan->impl.dec_plan));
+  for (int i = 0; i < kMaxOctaves; ++i)
+    if (plan->impl.resp_plan[i]) gtc_cqt_plan_destroy(reinterpret_cast<gtc_plan*>(plan->impl.resp_plan[i]));
   delete plan;
   return GTC_OK;
 }
@@ -451,6 +644,14 @@ static int scqt_run(const gtc_splan* plan, const void* d_audio, int sample_forma
   GTC_REQUIRE(workspace_bytes >= w.total, GTC_E_NOMEM, "gtc_scqt: workspace of %zu bytes, %zu needed", workspace_bytes, w.total);
   GTC_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 15) == 0, GTC_E_ARG, "gtc_scqt: workspace must be 16-byte aligned");
   char* ws = static_cast<char*>(d_workspace);
+  if (p.use_tc && !complex_out && max_len > 0) {
+    GTC_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, GTC_E_ARG, "gtc_scqt: workspace must be 256-byte aligned");
+    if (sample_format == GTC_SAMPLES_PCM16)
+      return run_structured_tc(p, (const int16_t*)d_audio, d_seg_start, d_seg_valid, d_seg_len, n_seg, max_len, d_out, ws, w, power, amin,
+                               top_db, cut_db, floor_db, st);
+    return run_structured_tc(p, (const float*)d_audio, d_seg_start, d_seg_valid, d_seg_len, n_seg, max_len, d_out, ws, w, power, amin,
+                             top_db, cut_db, floor_db, st);
+  }
   if (sample_format == GTC_SAMPLES_PCM16)
     return run_structured(p, (const int16_t*)d_audio, d_seg_start, d_seg_valid, d_seg_len, n_seg, max_len, d_out, complex_out, ws, w,
                           power, amin, top_db, cut_db, floor_db, st);

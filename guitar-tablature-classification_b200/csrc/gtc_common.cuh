@@ -1,6 +1,7 @@
 // Shared helpers for libgtc.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -54,6 +55,21 @@ __device__ __forceinline__ int find_clip(const int64_t* __restrict__ off, int n,
     if (__ldg(off + mid) <= g) lo = mid; else hi = mid;
   }
   return lo;
+}
+
+__device__ __host__ __forceinline__ int halved_len(int n, int times) {
+  for (int i = 0; i < times; ++i) n = (n + 1) >> 1;
+  return n;
+}
+// frames librosa keeps (__trim_stack): min over octaves of 1 + len_i // hop_i
+__device__ __host__ __forceinline__ int cqt_frames_of(int len, int hop, int n_oct) {
+  int t = 0x7fffffff;
+  for (int i = 0; i < n_oct; ++i) {
+    const int f = 1 + len / hop;
+    t = f < t ? f : t;
+    if ((hop & 1) == 0) { hop >>= 1; len = (len + 1) >> 1; }
+  }
+  return t;
 }
 
 // ---- dB finish of one segment (cqt.py:56-58), shared by finish_db_kernel and the fused tcgen05 epilogue so that both
@@ -155,6 +171,30 @@ struct OpLayout {
   }
 };
 
+// ---- "slotted" M operand of the tensor-core engine (structured CQT, cqt_structured.cu).  The rows of the GEMM are windows
+// of per-segment signals stored as fp16 hi/lo planes: segment s owns `stride` samples starting at base + s * stride, row j
+// of a segment is the window starting at j * row_step samples (windows overlap: the TMA tensor map simply has a row stride
+// smaller than the row length).  A 128-row tile is 16 segments x 8 consecutive rows (3-D TMA box), so short and ragged
+// segments waste at most 7 rows each.  slot_mode: 1 = 2:1 decimator (output: the next octave's hi/lo planes, samples
+// beyond the segment's length zeroed), 2 = octave response (output: |C|^2 into [seg][bin][t] + the segment maximum).
+struct SlotArgs {
+  int slot_mode;            // 0 = off
+  int jgroups;              // groups of 8 rows per segment
+  int64_t n_slots;          // segments
+  // mode 1
+  __half* out_hi;
+  __half* out_lo;
+  int64_t out_stride;       // samples per segment of the output planes
+  int64_t out_base;         // first sample of segment 0 in the output planes
+  const int32_t* seg_len;   // [n_slots] full-rate lengths
+  int stage_out;            // the output is octave `stage_out`: its valid length is seg_len halved stage_out times
+  float plane_scale;        // power-of-two scale of the planes (the fp16x2 engine's x_scale)
+  // mode 2
+  float* out;               // [n_slots][n_bins][t_max] |C|^2
+  float* segmax;            // [n_slots]
+  int n_bins, bin_lo, bin_cnt, t_max, hop0, n_oct;
+};
+
 // ---- segment-operator plan (cqt_api.cu) -------------------------------------------------------------------
 struct PlanImpl {
   int device;
@@ -192,6 +232,9 @@ int launch_gemm_simt(const PlanImpl& p, const float* d_xhi, const float* d_xlo, 
                      float* d_mag2, float* d_cplx, float* d_rowmax, cudaStream_t st);
 int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int64_t n_rows_pad, int64_t n_rows_alloc,
                    float* d_mag2, float* d_cplx, float* d_rowmax, const FinishArgs& fin, cudaStream_t st);
+// structured CQT: GEMM of slotted rows (3-D tensor maps over the hi/lo planes) against plan `p`'s operator
+int launch_gemm_tc_slots(const PlanImpl& p, const __half* x_hi, const __half* x_lo, int64_t x_first, int64_t x_stride,
+                         int64_t row_step, int rows_per_slot, const SlotArgs& slots, cudaStream_t st);
 int tc_plan_init(PlanImpl& p);
 int tc_pick_plain_width(int n_out);                       // tile width of the plain row order
 bool tc_has_frame_major_kernel(int nc, int n_frames);     // is gemm_tc_kernel instantiated for this frame-major tile?
