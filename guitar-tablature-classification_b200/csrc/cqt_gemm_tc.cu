@@ -37,6 +37,17 @@ constexpr uint32_t X_TILE_BYTES = TBM * TBK * 4;        // 128 rows x TKB_BYTES 
 constexpr uint32_t OP_TILE_BYTES = TMAXN * TBK * 4;     // 256 rows x TKB_BYTES   (16 KB at 64 B; NC rows used)
 constexpr uint32_t STAGE_BYTES = 2 * X_TILE_BYTES + 2 * OP_TILE_BYTES;   // hi + lo of both operands (48 KB at 64 B)
 constexpr uint32_t TC_SMEM_BYTES = TSTAGES * STAGE_BYTES + 1024 /*align slack*/;
+constexpr int TMAXSTAGES = 8;
+// Ring geometry per tile width: a stage holds hi + lo of 128 X rows and of NC operator rows, and the ring is as deep as the
+// shared memory allows (at most 8 stages).  NC = 240: 46 KB x 4; NC = 128 (decimator): 32 KB x 6; NC = 32 (octave response):
+// 20 KB x 8 -- the narrow kernels have K = 4..22 k-blocks per tile and live on load latency, so depth is what they need.
+template <int NC>
+struct Ring {
+  static constexpr uint32_t op_bytes = ((uint32_t)NC * TBK * 4 + 1023u) & ~1023u;
+  static constexpr uint32_t stage_bytes = 2 * X_TILE_BYTES + 2 * op_bytes;
+  static constexpr int fit = (int)((TC_SMEM_BYTES - 1024) / stage_bytes);
+  static constexpr int stages = fit > TMAXSTAGES ? TMAXSTAGES : fit;
+};
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 #ifndef TC_MAXNREG
@@ -227,26 +238,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   static_assert(NC % 16 == 0 && NC <= TMAXN && H % 8 == 0, "unsupported tile width");
   static_assert(TFM == 0 || NC % (TFM > 0 ? 2 * TFM : 1) == 0, "a frame-major tile holds whole bins x TFM frames");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bars[2 * TSTAGES + 4];
+  constexpr int NSTAGES = Ring<NC>::stages;
+  constexpr uint32_t STAGE_B = Ring<NC>::stage_bytes, OP_B = Ring<NC>::op_bytes;
+  __shared__ __align__(8) uint64_t s_bars[2 * TMAXSTAGES + 4];
   __shared__ uint32_t s_tmem_slot;
   __shared__ int s_block_done;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // stage s : [Xhi][Xlo][Ohi][Olo]   (X_TILE_BYTES, X_TILE_BYTES, OP_TILE_BYTES, OP_TILE_BYTES)
-  auto st_xhi = [&](int s) { return smem_base + s * STAGE_BYTES; };
-  auto st_xlo = [&](int s) { return smem_base + s * STAGE_BYTES + X_TILE_BYTES; };
-  auto st_ohi = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * X_TILE_BYTES; };
-  auto st_olo = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * X_TILE_BYTES + OP_TILE_BYTES; };
+  auto st_xhi = [&](int s) { return smem_base + s * STAGE_B; };
+  auto st_xlo = [&](int s) { return smem_base + s * STAGE_B + X_TILE_BYTES; };
+  auto st_ohi = [&](int s) { return smem_base + s * STAGE_B + 2 * X_TILE_BYTES; };
+  auto st_olo = [&](int s) { return smem_base + s * STAGE_B + 2 * X_TILE_BYTES + OP_B; };
   const uint32_t bar_base = smem_u32(s_bars);
   auto bar_full = [&](int s) { return bar_base + 8 * s; };
-  auto bar_empty = [&](int s) { return bar_base + 8 * (TSTAGES + s); };
-  auto bar_tfull = [&](int a) { return bar_base + 8 * (2 * TSTAGES + a); };
-  auto bar_tempty = [&](int a) { return bar_base + 8 * (2 * TSTAGES + 2 + a); };
+  auto bar_empty = [&](int s) { return bar_base + 8 * (NSTAGES + s); };
+  auto bar_tfull = [&](int a) { return bar_base + 8 * (2 * NSTAGES + a); };
+  auto bar_tempty = [&](int a) { return bar_base + 8 * (2 * NSTAGES + 2 + a); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TSTAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int s = 0; s < NSTAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -295,7 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 #ifndef TC_EXP_SKIP_OLO
           tma_load_2d(st_olo(stage), &tm_olo, bar_full(stage), kb * EPK, n0);
 #endif
-          if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -333,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
               }
             }
             umma_commit(bar_empty(stage));                  // frees the smem slot when these MMAs retire
-            if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
+            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
           }
           umma_commit(bar_tfull(acc));                      // this split's partial sums are complete
         }
@@ -420,8 +433,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         const int64_t slot = 16 * (int64_t)sg + (rho >> 3);
         const int j = 8 * jg + (rho & 7);
         const bool live = slot < sl.n_slots;
-        const int len0 = live ? __ldg(sl.seg_len + slot) : 0;
         if (SLOT == 1) {
+          const int len0 = live ? __ldg(sl.seg_len + slot) : 0;
           // decimator: row j holds outputs k = j * NC + n of the next octave; beyond the octave's length -> zeros (librosa
           // fixes the length to ceil(n / 2), and the next stage must see a zero-extended signal)
           const int valid = halved_len(len0, sl.stage_out);
@@ -445,7 +458,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         } else {
           // response: row j = frame t of the segment, columns = (bin, {re, im}) of the octave's filters
           const int t = j;
-          const bool valid = live && t < cqt_frames_of(len0, sl.hop0, sl.n_oct);
+          const bool valid = live && t < __ldg(sl.seg_frames + slot);      // frames librosa keeps (precomputed: 7 divisions)
           float mx = 0.f;
 #pragma unroll
           for (int c = 0; c < H; c += 2) {

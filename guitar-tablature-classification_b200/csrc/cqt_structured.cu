@@ -302,8 +302,15 @@ struct PadList {
   __half* plane[2 * kMaxOctaves];
   int64_t tail_at[2 * kMaxOctaves], tail_len[2 * kMaxOctaves];
   int n;
+  const int32_t* seg_len;       // also: frames kept per segment, for the response epilogues
+  int32_t* seg_frames;
+  int64_t n_seg;
+  int hop, n_oct;
 };
 __global__ void __launch_bounds__(256) pad_zero_kernel(const PadList pl) {
+  if (blockIdx.y == 0)
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < pl.n_seg; s += (int64_t)gridDim.x * blockDim.x)
+      pl.seg_frames[s] = frames_of(__ldg(pl.seg_len + s), pl.hop, pl.n_oct);
   for (int i = blockIdx.y; i < pl.n; i += gridDim.y) {
     __half* p = pl.plane[i];
     const int64_t total = kPlaneFront + pl.tail_len[i];
@@ -345,7 +352,7 @@ static inline size_t dec_smem_bytes(int n_taps) {
 struct SWorkspace {
   OctaveBufs bufs;
   TcGeom tc;
-  size_t off_segmax, total, total_tc;
+  size_t off_segmax, off_segframes, total, total_tc;
 };
 
 static SWorkspace s_layout(const SPlanImpl& p, int64_t n_seg, int64_t max_len) {
@@ -354,6 +361,7 @@ static SWorkspace s_layout(const SPlanImpl& p, int64_t n_seg, int64_t max_len) {
   size_t o = 0;
   auto take = [&](size_t b) { size_t at = o; o += (b + 1023) & ~(size_t)1023; return at; };
   w.off_segmax = take((size_t)(n_seg > 0 ? n_seg : 1) * sizeof(float));
+  w.off_segframes = take((size_t)(n_seg > 0 ? n_seg : 1) * sizeof(int32_t));
   if (p.use_tc && n_seg > 0 && max_len > 0) {             // tensor path: hi/lo planes of every octave, after the maxima
     size_t o_tc = o;
     auto take_tc = [&](size_t b) { size_t at = o_tc; o_tc += (b + 1023) & ~(size_t)1023; return at; };
@@ -381,6 +389,7 @@ static int run_structured_tc(const SPlanImpl& p, const In* d_audio, const int64_
                              float power, float amin, float top_db, float cut_db, float floor_db, cudaStream_t st) {
   const TcGeom& g = w.tc;
   float* segmax = reinterpret_cast<float*>(ws + w.off_segmax);
+  int32_t* seg_frames = reinterpret_cast<int32_t*>(ws + w.off_segframes);
   const int t_max = frames_of((int)max_len, p.hop, p.n_oct);
   GTC_CUDA_CHECK(cudaMemsetAsync(segmax, 0, (size_t)n_seg * sizeof(float), st));
   auto hi = [&](int i) { return reinterpret_cast<__half*>(ws + g.off_hi[i]); };
@@ -394,6 +403,7 @@ static int run_structured_tc(const SPlanImpl& p, const In* d_audio, const int64_
         pl.tail_at[2 * i + h] = kPlaneFront + n_seg * g.S[i];
         pl.tail_len[2 * i + h] = g.plane_elems[i] - (kPlaneFront + n_seg * g.S[i]);
       }
+    pl.seg_len = d_seg_len; pl.seg_frames = seg_frames; pl.n_seg = n_seg; pl.hop = p.hop; pl.n_oct = p.n_oct;
     pad_zero_kernel<<<dim3(8, (unsigned)pl.n), 256, 0, st>>>(pl);
     GTC_CUDA_CHECK(cudaGetLastError());
   }
@@ -408,6 +418,7 @@ static int run_structured_tc(const SPlanImpl& p, const In* d_audio, const int64_
   memset(&sl, 0, sizeof(sl));
   sl.n_slots = n_seg;
   sl.seg_len = d_seg_len;
+  sl.seg_frames = seg_frames;
   sl.plane_scale = kPlaneScale;
   const PlanImpl& dec = *reinterpret_cast<const PlanImpl*>(p.dec_plan);
   for (int i = 0; i + 1 < p.n_oct; ++i) {                 // octave i+1 = 2:1 decimation of octave i

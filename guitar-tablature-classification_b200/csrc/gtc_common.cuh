@@ -187,6 +187,7 @@ struct SlotArgs {
   int64_t out_stride;       // samples per segment of the output planes
   int64_t out_base;         // first sample of segment 0 in the output planes
   const int32_t* seg_len;   // [n_slots] full-rate lengths
+  const int32_t* seg_frames;   // [n_slots] frames librosa keeps for each segment (mode 2)
   int stage_out;            // the output is octave `stage_out`: its valid length is seg_len halved stage_out times
   float plane_scale;        // power-of-two scale of the planes (the fp16x2 engine's x_scale)
   // mode 2
