@@ -174,3 +174,37 @@ def test_argument_errors(splan):
                                           C.c_void_p(le.data_ptr()), 1, 100, C.c_void_p(a.data_ptr()), C.c_void_p(small.data_ptr()), 16,
                                           4.0, 1e-5, 80.0, -60.0, -120.0, None)
     assert rc == _lib.load().gtc_version() * 0 - 3               # GTC_E_NOMEM
+
+
+def test_tensor_core_path_equals_fp32_simt_path(lib, monkeypatch):
+    """dB features: the tcgen05 evaluation (Toeplitz decimator + slotted response GEMMs on fp16 hi/lo planes, the default)
+    against the fp32 CUDA-core evaluation of the same plan tables (GTC_SCQT_SIMT=1 at plan creation), on ragged whole
+    clips at 44.1 kHz (n_fft 256, 8 octaves), 17 clips so that the 16-segment tile groups have a ragged tail."""
+    from gtc_b200 import ops, CqtRecipe
+    dev = torch.device("cuda")
+    r = CqtRecipe(sr=44100.0)
+    lens = [44100, 30001, 8820, 1500, 256, 70000] + [12000 + 977 * i for i in range(11)]
+    clips = [make_test_audio(n, seed=150 + i, sr=44100.0) for i, n in enumerate(lens)]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    st, va, le = seg_tables(off[:-1].tolist(), lens, lens, dev)
+    audio = torch.from_numpy(np.concatenate(clips)).to(dev)
+    p_tc = ops.StructuredCqtPlan(r)
+    a = p_tc.segments_db(audio, st, va, le, max(lens)).cpu().numpy()
+    monkeypatch.setenv("GTC_SCQT_SIMT", "1")
+    p_simt = ops.StructuredCqtPlan(r)
+    monkeypatch.delenv("GTC_SCQT_SIMT")
+    b = p_simt.segments_db(audio, st, va, le, max(lens)).cpu().numpy()
+    assert a.shape == b.shape == (len(lens), 96, p_tc.frames(max(lens)))
+    for i, n in enumerate(lens):
+        T = p_tc.frames(n)
+        x, y = a[i, :, :T], b[i, :, :T]
+        both = (x > -59.9) & (y > -59.9)
+        assert both.sum() > 0 and np.abs(x - y)[both].max() < 0.01, f"clip {i}"
+        assert ((x == -120) != (y == -120)).mean() < 2e-3            # elements within rounding of the -60 dB cut
+        assert np.array_equal(a[i, :, T:], b[i, :, T:])                # frames past the clip's own length: same filler
+    # 16-bit PCM input takes the same path
+    pcm = torch.clamp(torch.round(audio * 32768.0), -32768, 32767).to(torch.int16)
+    c = p_tc.segments_db(pcm, st, va, le, max(lens)).cpu().numpy()
+    d = p_tc.segments_db(pcm.to(torch.float32) / 32768.0, st, va, le, max(lens)).cpu().numpy()
+    assert np.array_equal(c, d)
+    p_tc.close(); p_simt.close()
