@@ -48,9 +48,9 @@ hbm_row("frame_kernel<half,short>", ms, n_rows * 2205 * 2 + 2 * rows_alloc * kp 
 plan.frame(audio, co, so, n_seg, ws)
 ms_c = timeit(lambda: plan.contract_db(co, so, n_seg, db, ws))
 flop = 3 * 2.0 * n_rows * 960 * 2 * kp
-rows.append(f"| `gemm_tc_kernel<240,0,1>` + `finish_db_kernel` | tensor | {ms_c * 1e3:.1f} | {flop / 1e9:.0f} GFLOP fp16 issued "
+rows.append(f"| `gemm_tc_kernel<240,0,1,5>` + `finish_db_kernel` | tensor | {ms_c * 1e3:.1f} | {flop / 1e9:.0f} GFLOP fp16 issued "
             f"({flop / 3e9:.0f} fp32-equivalent) | {flop / (ms_c * 1e-3) / 1e12:.0f} TFLOP/s | {flop / (ms_c * 1e-3) / 1e12 / TC:.2f} of cuBLAS bf16 burst | "
-            f"two launches timed together; finish alone is 28.7 us in the ncu launch list (72 MB through L2) |")
+            f"two launches timed together; finish alone is 19.5 us per 28 200-row chunk in the ncu launch list (profiles/r02e_gemm_finish_ab.md) |")
 on, du, pi, eoff = synth.note_events([30.0] * n_clips, seed=2)
 t_ = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 times = np.concatenate([(np.arange(299) + 0.5) * (30.0 / 299)] * n_clips)
