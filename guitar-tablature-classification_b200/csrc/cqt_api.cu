@@ -149,6 +149,19 @@ extern "C" int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int 
   for (int t = 0; t < n_frames; ++t)
     for (int b = 0; b < n_bins; ++b)
       for (int c = 0; c < 2; ++c) lib_row[(t * n_bins + b) * 2 + c] = lay.gemm_row(b, t, c);
+  // non-zero map of the operator at the tensor engine's granularity (row group x k-block), for its zero-skipping schedule
+  p.grp_rows = p.bins_per_tile > 0 ? 2 * p.bins_per_tile : 16;
+  const int n_kblocks = p.k_total / p.kb_elems;
+  std::vector<uint8_t> nz;
+  if (tensor && p.nc % p.grp_rows == 0) {
+    nz.assign((size_t)(p.n_pad / p.grp_rows) * n_kblocks, 0);
+    for (int n = 0; n < p.n_out; ++n) {
+      uint8_t* row = &nz[(size_t)(lib_row[n] / p.grp_rows) * n_kblocks];
+      const float* src = h_operator + (size_t)n * seg_len;
+      for (int j = 0; j < seg_len; ++j)
+        if (src[j] != 0.f) row[at_of(j) / p.kb_elems] = 1;
+    }
+  }
   if (half) {
     // fp16x2: A * 2^s = hi + lo with s such that max|A| * 2^s <= 2^13; absolute quantisation error <= 2^-25 (fp16
     // subnormal spacing / 2) against row maxima of ~2^13, i.e. < 2^-36 relative -- see DESIGN.md 3.1
@@ -187,7 +200,8 @@ extern "C" int gtc_cqt_plan_create(gtc_plan** out, int device, int seg_len, int 
       return rc;
     }
   }
-  if (tensor && (rc = tc_plan_init(p)) != GTC_OK) {
+  const int ksplit = (p.tc_kb_per_split > 0 ? p.tc_kb_per_split : 8) * (128 / TC_KB_BYTES);
+  if (tensor && (rc = tc_plan_init(p, nz.empty() || getenv("GTC_TC_DENSE") ? nullptr : nz.data(), ksplit)) != GTC_OK) {
     gtc_cqt_plan_destroy(plan);
     return rc;
   }

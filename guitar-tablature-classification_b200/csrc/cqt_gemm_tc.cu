@@ -21,7 +21,9 @@
 //                              values) stored straight to global memory
 // The second audio row of a segment (hop = window/2, cqt.py:26-27) is just the TMA row coordinate + p.
 #include <cuda.h>
+#include <stdlib.h>
 #include <type_traits>
+#include <vector>
 #include "gtc_common.cuh"
 
 namespace gtc {
@@ -68,6 +70,14 @@ struct TcParams {
   float* rowmax;         // [rows]
   FinishArgs fin;        // fin.out_db != null: the CTA that completes the last N tile of a 128-row block also does its dB finish
   SlotArgs slots;        // SLOT > 0 kernels: slotted rows of the structured CQT
+  // zero-skipping schedule (null = every k-block against the whole N tile).  Entry = kb | g0 << 16 | ng << 24: multiply k-block
+  // kb with the ng row groups starting at group g0 of the tile; the first entry of every K split covers the whole tile
+  // (it zero-initialises the accumulator stage).  Tiles are then ordered by passes over the N tiles, heaviest first.
+  const uint32_t* sched;
+  const int* sched_len;
+  const int* chunk_order;
+  const CUtensorMap* op_maps;   // [n_groups][2] operator boxes of (g + 1) * grp_rows rows (hi, lo), device memory
+  int sched_pitch, grp_rows, rotate;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -228,7 +238,8 @@ __device__ __forceinline__ void fused_finish_block(const TcParams& prm, int64_t 
 // the two kernels measured SLOWER than back to back -- both live on L2 bandwidth -- profiles/r01j_coresident.md.)
 // TFM > 0: frame-major tiles (OpLayout, gtc_common.cuh) of a TFM-frame recipe: NC = 2 * TFM * bins_per_tile; 0: plain rows.
 // SLOT > 0: the M operand is slotted (SlotArgs, gtc_common.cuh): 1 = decimator epilogue, 2 = response epilogue.
-template <int NC, bool kComplex, bool kHalf, int TFM, int SLOT = 0>
+// SCHED: multiply every k-block only with the row groups (frames) of the tile that are non-zero on it (TcParams::sched).
+template <int NC, bool kComplex, bool kHalf, int TFM, int SLOT = 0, bool SCHED = false>
 __global__ void __maxnreg__(TC_MAXNREG)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo,
@@ -243,6 +254,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   __shared__ __align__(8) uint64_t s_bars[2 * TMAXSTAGES + 4];
   __shared__ uint32_t s_tmem_slot;
   __shared__ int s_block_done;
+  // the schedule lives in shared memory: the producer and the MMA issuer read one entry per k-block on their critical path,
+  // and with 193 KB of the SM carved out as shared memory a global load is an L2 round trip (~300 cycles x 138 entries)
+  constexpr int kSchedMax = 4096;
+  __shared__ uint32_t s_sched[SCHED ? kSchedMax : 1];
+  __shared__ int s_sched_len[SCHED ? 16 : 1];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // stage s : [Xhi][Xlo][Ohi][Olo]   (X_TILE_BYTES, X_TILE_BYTES, OP_TILE_BYTES, OP_TILE_BYTES)
   auto st_xhi = [&](int s) { return smem_base + s * STAGE_B; };
@@ -264,6 +280,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&s_tmem_slot), 512);
+  if (SCHED) {
+    for (int i = threadIdx.x; i < prm.n_chunks * prm.sched_pitch; i += blockDim.x) s_sched[i] = __ldg(prm.sched + i);
+    if (threadIdx.x < prm.n_chunks) s_sched_len[threadIdx.x] = __ldg(prm.sched_len + threadIdx.x);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -272,6 +292,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   const int nkb = prm.parts * prm.kb_per_part;
   const int n_splits = (nkb + prm.kb_per_split - 1) / prm.kb_per_split;
   const int64_t n_tiles = prm.m_tiles * prm.n_chunks;
+  // tile -> (row block, N tile): row-block major, so that the N tiles of a row block run side by side on adjacent CTAs and
+  // share their X rows in L2.  With a schedule the N tiles cost differently (top octaves ~0.2, low octaves 1), so the N tile
+  // index is rotated by the CTA's iteration: every CTA sees every tile type in turn instead of always the same one.
+  // (Passes over the N tiles in order of cost balance better on paper and measured 14 % SLOWER: each pass re-reads all X
+  // rows from HBM -- 4.7 TB/s in the dense passes.)
+  auto tile_of = [&](int64_t tile, int iter, int64_t& m_tile, int& chunk) {
+    m_tile = tile / prm.n_chunks;
+    chunk = (int)(tile - m_tile * prm.n_chunks);
+    if (SCHED && prm.rotate) chunk = (chunk + iter) % prm.n_chunks;
+  };
 #ifdef TC_EXP_SKIP_OLO   // timing experiment only (wrong results): is the kernel bound by operand delivery from L2?
   constexpr uint32_t stage_tx = 2 * X_TILE_BYTES + 1 * (uint32_t)NC * TBK * 4;
 #else
@@ -286,14 +316,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_ohi)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_olo)) : "memory");
       int stage = 0; uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t m_tile = tile / prm.n_chunks;
-        const int chunk = (int)(tile - m_tile * prm.n_chunks);
+      int iter = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+        int64_t m_tile; int chunk;
+        tile_of(tile, iter, m_tile, chunk);
         const int row0 = (int)(m_tile * TBM);
         const int n0 = chunk * NC;
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int n_ent = SCHED ? s_sched_len[chunk] : nkb;
+        for (int e = 0; e < n_ent; ++e) {
+          int kb = e, g0 = 0, rows = NC;
+          if (SCHED) {
+            const uint32_t w = s_sched[chunk * prm.sched_pitch + e];
+            kb = (int)(w & 0xffffu); g0 = (int)((w >> 16) & 0xffu); rows = (int)(w >> 24) * prm.grp_rows;
+          }
           mbar_wait(bar_empty(stage), phase ^ 1);
-          mbar_expect_tx(bar_full(stage), stage_tx);
+          mbar_expect_tx(bar_full(stage), rows == NC ? stage_tx : 2 * X_TILE_BYTES + 2 * (uint32_t)rows * TBK * 4);
           const int p = kb / prm.kb_per_part;
           const int kx = (kb - p * prm.kb_per_part) * EPK;
           if (SLOT == 0) {
@@ -304,10 +341,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             tma_load_3d(st_xhi(stage), &tm_xhi, bar_full(stage), kx, 8 * jg, 16 * sg);
             tma_load_3d(st_xlo(stage), &tm_xlo, bar_full(stage), kx, 8 * jg, 16 * sg);
           }
-          tma_load_2d(st_ohi(stage), &tm_ohi, bar_full(stage), kb * EPK, n0);
+          if (!SCHED || rows == NC) {
+            tma_load_2d(st_ohi(stage), &tm_ohi, bar_full(stage), kb * EPK, n0);
 #ifndef TC_EXP_SKIP_OLO
-          tma_load_2d(st_olo(stage), &tm_olo, bar_full(stage), kb * EPK, n0);
+            tma_load_2d(st_olo(stage), &tm_olo, bar_full(stage), kb * EPK, n0);
 #endif
+          } else {                                           // only the row groups whose support reaches this k-block
+            const CUtensorMap* om = prm.op_maps + 2 * (rows / prm.grp_rows - 1);
+            tma_load_2d(st_ohi(stage), om, bar_full(stage), kb * EPK, n0 + g0 * prm.grp_rows);
+            tma_load_2d(st_olo(stage), om + 1, bar_full(stage), kb * EPK, n0 + g0 * prm.grp_rows);
+          }
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -319,15 +362,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       const uint32_t idesc = make_idesc(kHalf ? 0u : 2u, TBM, NC);
       int stage = 0; uint32_t phase = 0;
       uint32_t it = 0;                                       // accumulator-stage use counter (one per K split)
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        int kb = 0;
-        for (int sp = 0; sp < n_splits; ++sp, ++it) {
+      int iter = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+        int64_t m_tile; int chunk;
+        tile_of(tile, iter, m_tile, chunk);
+        const int n_ent = SCHED ? s_sched_len[chunk] : nkb;
+        const int n_sp = SCHED ? (n_ent + prm.kb_per_split - 1) / prm.kb_per_split : n_splits;
+        int kb = 0;                                          // entry index
+        for (int sp = 0; sp < n_sp; ++sp, ++it) {
           const int acc = (int)(it & 1u);
           mbar_wait(bar_tempty(acc), ((it >> 1) & 1u) ^ 1u); // epilogue drained this accumulator stage
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (uint32_t)acc * TMAXN;
-          const int kb_end = min(nkb, kb + prm.kb_per_split);
+          uint32_t tmem_d = tmem_base + (uint32_t)acc * TMAXN;
+          const int kb_end = min(n_ent, kb + prm.kb_per_split);
           for (int first = 1; kb < kb_end; ++kb, first = 0) {
+            uint32_t idesc_e = idesc;
+            tmem_d = tmem_base + (uint32_t)acc * TMAXN;
+            if (SCHED) {                                     // N = the row groups this k-block touches, at their accumulator columns
+              const uint32_t w = s_sched[chunk * prm.sched_pitch + kb];
+              const int rows = (int)(w >> 24) * prm.grp_rows;
+              if (rows != NC) {
+                idesc_e = make_idesc(kHalf ? 0u : 2u, TBM, rows);
+                tmem_d += (uint32_t)(((w >> 16) & 0xffu) * prm.grp_rows);
+              }
+            }
             mbar_wait(bar_full(stage), phase);
             tc_fence_after();
             const uint64_t dxh = make_swizzle_desc(st_xhi(stage)), dxl = make_swizzle_desc(st_xlo(stage));
@@ -336,13 +394,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             for (int k = 0; k < TBK / TUMMA_K; ++k) {
               const uint64_t adv = (uint64_t)((k * TUMMA_K * 4) >> 4);   // +32 B per k-step inside the swizzle row
               if (kHalf) {
-                umma_f16(tmem_d, dxh + adv, doh + adv, idesc, (first && k == 0) ? 0u : 1u);
-                umma_f16(tmem_d, dxl + adv, doh + adv, idesc, 1u);
-                umma_f16(tmem_d, dxh + adv, dol + adv, idesc, 1u);
+                umma_f16(tmem_d, dxh + adv, doh + adv, idesc_e, (first && k == 0) ? 0u : 1u);
+                umma_f16(tmem_d, dxl + adv, doh + adv, idesc_e, 1u);
+                umma_f16(tmem_d, dxh + adv, dol + adv, idesc_e, 1u);
               } else {
-                umma_tf32(tmem_d, dxh + adv, doh + adv, idesc, (first && k == 0) ? 0u : 1u);
-                umma_tf32(tmem_d, dxl + adv, doh + adv, idesc, 1u);
-                umma_tf32(tmem_d, dxh + adv, dol + adv, idesc, 1u);
+                umma_tf32(tmem_d, dxh + adv, doh + adv, idesc_e, (first && k == 0) ? 0u : 1u);
+                umma_tf32(tmem_d, dxl + adv, doh + adv, idesc_e, 1u);
+                umma_tf32(tmem_d, dxh + adv, dol + adv, idesc_e, 1u);
               }
             }
             umma_commit(bar_empty(stage));                  // frees the smem slot when these MMAs retire
@@ -359,13 +417,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     const int half = (warp - 2) >> 2;                        // which NC/2 column half
     const int n_mag = prm.n_out >> 1;
     uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t m_tile = tile / prm.n_chunks;
-      const int chunk = (int)(tile - m_tile * prm.n_chunks);
+    int iter = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+      int64_t m_tile; int chunk;
+      tile_of(tile, iter, m_tile, chunk);
       const int64_t row = m_tile * TBM + q * 32 + lane;
       const int n0 = chunk * NC + half * H;
+      const int n_sp = SCHED ? (s_sched_len[chunk] + prm.kb_per_split - 1) / prm.kb_per_split : n_splits;
       float sum[H];
-      for (int sp = 0; sp < n_splits; ++sp, ++it) {
+      for (int sp = 0; sp < n_sp; ++sp, ++it) {
         const int acc = (int)(it & 1u);
         mbar_wait(bar_tfull(acc), (it >> 1) & 1u);
         tc_fence_after();
@@ -637,7 +697,7 @@ static int for_plan_kernels(const PlanImpl& p, int cplx, int half, F&& f) {
   }
 }
 
-int tc_plan_init(PlanImpl& p) {
+int tc_plan_init(PlanImpl& p, const uint8_t* h_nz, int kb_per_split) {
   CUtensorMap* maps = new CUtensorMap[2];
   p.tmap_op_hi = &maps[0];
   p.tmap_op_lo = &maps[1];
@@ -645,15 +705,79 @@ int tc_plan_init(PlanImpl& p) {
   if (rc != GTC_OK) return rc;
   rc = encode_2d(&maps[1], p.d_op_lo, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)p.nc, p.elem_bytes);
   if (rc != GTC_OK) return rc;
-  return for_plan_kernels(p, -1, -1, [](auto kern) -> int {
+  rc = for_plan_kernels(p, -1, -1, [](auto kern) -> int {
     GTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     return GTC_OK;
   });
+  if (rc != GTC_OK || h_nz == nullptr || p.bins_per_tile == 0 || p.elem_bytes != 2) return rc;   // scheduled kernels: frame-major fp16x2 plans
+
+  // ---- zero-skipping schedule.  Per N tile: the k-blocks with any non-zero entry and, for each, the contiguous range of row
+  //      groups it touches (a group = one frame of a frame-major tile: an operator row is non-zero on a window of samples
+  //      around its frame, so the range is 1-2 frames wide in the top octaves and all of them in the low ones).
+  const int n_chunks = (int)ceil_div(p.n_out, p.nc), n_grp = p.nc / p.grp_rows, nkb = p.k_total / p.kb_elems;
+  const int exp_mode = getenv("GTC_TC_SCHED_MODE") ? atoi(getenv("GTC_TC_SCHED_MODE")) : 0;   // experiments: 1 = whole-tile entries, 2 = no rotation of the N tiles
+  p.sched_pass_order = (exp_mode & 2) ? 0 : 1;
+  if (n_grp < 2 || n_grp > 255 || nkb > 65535) return GTC_OK;
+  std::vector<uint32_t> sched((size_t)n_chunks * nkb, 0);
+  std::vector<int> len(n_chunks, 0), order(n_chunks);
+  std::vector<long long> cost(n_chunks, 0);
+  long long work = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    int n = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      int g0 = -1, g1 = -1;
+      for (int g = 0; g < n_grp; ++g)
+        if (h_nz[(size_t)(c * n_grp + g) * nkb + kb]) { if (g0 < 0) g0 = g; g1 = g; }
+      if (g0 < 0) continue;                                         // nothing of this tile lives on this k-block
+      if (n % kb_per_split == 0 || (exp_mode & 1)) { g0 = 0; g1 = n_grp - 1; }   // first entry of a K split: whole tile, zero-initialises
+      sched[(size_t)c * nkb + n++] = (uint32_t)kb | ((uint32_t)g0 << 16) | ((uint32_t)(g1 - g0 + 1) << 24);
+      cost[c] += g1 - g0 + 1;
+    }
+    len[c] = n;
+    work += cost[c];
+    order[c] = c;
+  }
+  p.sched_fill = (float)work / (float)((long long)n_chunks * nkb * n_grp);
+  if (p.sched_fill > 0.92f && !(exp_mode & 1)) return GTC_OK;                          // nothing worth skipping: keep the dense loops
+  for (int i = 0; i < n_chunks; ++i)                                 // passes by decreasing cost (stable)
+    for (int j = i + 1; j < n_chunks; ++j)
+      if (cost[order[j]] > cost[order[i]]) { int t = order[i]; order[i] = order[j]; order[j] = t; }
+  std::vector<CUtensorMap> gm((size_t)2 * n_grp);
+  for (int g = 0; g < n_grp; ++g) {
+    rc = encode_2d(&gm[2 * g], p.d_op_hi, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)((g + 1) * p.grp_rows), p.elem_bytes);
+    if (rc == GTC_OK) rc = encode_2d(&gm[2 * g + 1], p.d_op_lo, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)((g + 1) * p.grp_rows), p.elem_bytes);
+    if (rc != GTC_OK) return rc;
+  }
+  GTC_CUDA_CHECK(cudaMalloc((void**)&p.d_sched, sched.size() * sizeof(uint32_t)));
+  GTC_CUDA_CHECK(cudaMemcpy(p.d_sched, sched.data(), sched.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  GTC_CUDA_CHECK(cudaMalloc((void**)&p.d_sched_len, n_chunks * sizeof(int)));
+  GTC_CUDA_CHECK(cudaMemcpy(p.d_sched_len, len.data(), n_chunks * sizeof(int), cudaMemcpyHostToDevice));
+  GTC_CUDA_CHECK(cudaMalloc((void**)&p.d_chunk_order, n_chunks * sizeof(int)));
+  GTC_CUDA_CHECK(cudaMemcpy(p.d_chunk_order, order.data(), n_chunks * sizeof(int), cudaMemcpyHostToDevice));
+  GTC_CUDA_CHECK(cudaMalloc(&p.d_op_maps, gm.size() * sizeof(CUtensorMap)));
+  GTC_CUDA_CHECK(cudaMemcpy(p.d_op_maps, gm.data(), gm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  p.sched_pitch = nkb;
+  p.sched_ksplit = kb_per_split;
+  if (p.bins_per_tile > 0 && p.elem_bytes == 2) {
+    if (p.nc == 240 && p.n_frames == 5) {
+      GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<240, false, true, 5, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+      GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<240, true, true, 5, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    } else {
+      GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<144, false, true, 9, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+      GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<144, true, true, 9, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    }
+  }
+  return GTC_OK;
 }
 
 void tc_plan_free(PlanImpl& p) {
   if (p.tmap_op_hi) delete[] reinterpret_cast<CUtensorMap*>(p.tmap_op_hi);
   p.tmap_op_hi = p.tmap_op_lo = nullptr;
+  if (p.d_sched) cudaFree(p.d_sched);
+  if (p.d_sched_len) cudaFree(p.d_sched_len);
+  if (p.d_chunk_order) cudaFree(p.d_chunk_order);
+  if (p.d_op_maps) cudaFree(p.d_op_maps);
+  p.d_sched = nullptr; p.d_sched_len = nullptr; p.d_chunk_order = nullptr; p.d_op_maps = nullptr;
 }
 
 int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int64_t n_rows_pad, int64_t n_rows_alloc,
@@ -676,11 +800,33 @@ int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int6
   prm.mag2 = d_mag2; prm.cplx = d_cplx; prm.rowmax = d_rowmax;
   prm.fin = fin;
   if (d_cplx != nullptr) prm.fin.out_db = nullptr;
+  memset(&prm.slots, 0, sizeof(prm.slots));
+  const bool use_sched = p.d_sched != nullptr && p.sched_ksplit == prm.kb_per_split && p.bins_per_tile > 0 && p.elem_bytes == 2 &&
+                         prm.n_chunks <= 16 && prm.n_chunks * p.sched_pitch <= 4096;
+  prm.sched = use_sched ? p.d_sched : nullptr;
+  prm.sched_len = p.d_sched_len;
+  prm.chunk_order = p.d_chunk_order;
+  prm.op_maps = reinterpret_cast<const CUtensorMap*>(p.d_op_maps);
+  prm.sched_pitch = p.sched_pitch;
+  prm.grp_rows = p.grp_rows;
   const int64_t n_tiles = prm.m_tiles * prm.n_chunks;
   const int64_t max_ctas = p.tc_max_ctas > 0 && p.tc_max_ctas < p.sm_count ? p.tc_max_ctas : p.sm_count;
   const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
   const CUtensorMap& tm_ohi = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_hi);
   const CUtensorMap& tm_olo = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_lo);
+  prm.rotate = use_sched && p.sched_pass_order && grid % (unsigned)prm.n_chunks == 0;
+  if (use_sched) {
+    const bool cplx = d_cplx != nullptr;
+    if (p.nc == 240 && p.n_frames == 5) {
+      if (cplx) gemm_tc_kernel<240, true, true, 5, 0, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
+      else      gemm_tc_kernel<240, false, true, 5, 0, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
+    } else {
+      if (cplx) gemm_tc_kernel<144, true, true, 9, 0, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
+      else      gemm_tc_kernel<144, false, true, 9, 0, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
+    }
+    GTC_CUDA_CHECK(cudaGetLastError());
+    return GTC_OK;
+  }
   rc = for_plan_kernels(p, d_cplx != nullptr ? 1 : 0, p.elem_bytes == 2 ? 1 : 0, [&](auto kern) -> int {
     kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
     return GTC_OK;

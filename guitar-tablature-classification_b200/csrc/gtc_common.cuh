@@ -222,6 +222,17 @@ struct PlanImpl {
   void* d_op_lo;    // [n_pad][k_total]  residual of the high part, same element type
   void* tmap_op_hi; // CUtensorMap storage (128 B each), tcgen05 engines only
   void* tmap_op_lo;
+  // ---- zero-skipping schedule of the tensor-core engines (cqt_gemm_tc.cu): per N tile the list of k-blocks that hold any
+  //      non-zero operator entry, each with the contiguous range of row groups (frames of a frame-major tile) it touches
+  int grp_rows;            // operator rows per group (2 * bins_per_tile, or 16 for plain tiles)
+  int sched_pitch;         // entries per N tile in d_sched
+  int sched_ksplit;        // k-blocks per accumulation split the schedule was built for (its first entry per split is dense)
+  uint32_t* d_sched;       // [n_chunks][sched_pitch]  kb | g0 << 16 | ng << 24 ; null = dense
+  int* d_sched_len;        // [n_chunks]
+  int* d_chunk_order;      // [n_chunks] N tiles by decreasing cost: tile T -> (chunk_order[T / m_tiles], T % m_tiles)
+  void* d_op_maps;         // CUtensorMap[n_groups][2] in device memory: operator boxes of (g + 1) * grp_rows rows, hi / lo
+  float sched_fill;        // scheduled tensor work / dense tensor work (1 = nothing to skip)
+  int sched_pass_order;    // 1: tiles in passes over the N tiles (heaviest first); 0: row-block major
 };
 
 // launchers (each enqueues on `st`, returns a GTC_* code); xhi/xlo element type follows PlanImpl::elem_bytes
@@ -236,7 +247,7 @@ int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int6
 // structured CQT: GEMM of slotted rows (3-D tensor maps over the hi/lo planes) against plan `p`'s operator
 int launch_gemm_tc_slots(const PlanImpl& p, const __half* x_hi, const __half* x_lo, int64_t x_first, int64_t x_stride,
                          int64_t row_step, int rows_per_slot, const SlotArgs& slots, cudaStream_t st);
-int tc_plan_init(PlanImpl& p);
+int tc_plan_init(PlanImpl& p, const uint8_t* h_nz /* [n_pad / grp_rows][k_blocks] non-zero flags, or null */, int kb_per_split);
 int tc_pick_plain_width(int n_out);                       // tile width of the plain row order
 bool tc_has_frame_major_kernel(int nc, int n_frames);     // is gemm_tc_kernel instantiated for this frame-major tile?
 void tc_plan_free(PlanImpl& p);
