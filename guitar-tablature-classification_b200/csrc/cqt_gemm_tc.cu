@@ -43,10 +43,11 @@ constexpr int TMAXSTAGES = 8;
 // Ring geometry per tile width: a stage holds hi + lo of 128 X rows and of NC operator rows, and the ring is as deep as the
 // shared memory allows (at most 8 stages).  NC = 240: 46 KB x 4; NC = 128 (decimator): 32 KB x 6; NC = 32 (octave response):
 // 20 KB x 8 -- the narrow kernels have K = 4..22 k-blocks per tile and live on load latency, so depth is what they need.
-template <int NC>
+// The decimator (SLOT = 1) multiplies MH = 2 row blocks per operator tile: 48 KB x 4.
+template <int NC, int MH = 1>
 struct Ring {
   static constexpr uint32_t op_bytes = ((uint32_t)NC * TBK * 4 + 1023u) & ~1023u;
-  static constexpr uint32_t stage_bytes = 2 * X_TILE_BYTES + 2 * op_bytes;
+  static constexpr uint32_t stage_bytes = 2 * MH * X_TILE_BYTES + 2 * op_bytes;     // MH row blocks of 128 share one operator tile
   static constexpr int fit = (int)((TC_SMEM_BYTES - 1024) / stage_bytes);
   static constexpr int stages = fit > TMAXSTAGES ? TMAXSTAGES : fit;
 };
@@ -249,8 +250,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   static_assert(NC % 16 == 0 && NC <= TMAXN && H % 8 == 0, "unsupported tile width");
   static_assert(TFM == 0 || NC % (TFM > 0 ? 2 * TFM : 1) == 0, "a frame-major tile holds whole bins x TFM frames");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int NSTAGES = Ring<NC>::stages;
-  constexpr uint32_t STAGE_B = Ring<NC>::stage_bytes, OP_B = Ring<NC>::op_bytes;
+  // MH: 128-row blocks that share one operator tile.  The decimator is bound by L2 -> SM operand delivery and every tile uses
+  // the SAME Toeplitz operator: two row blocks (32 segments x 8 rows) per operator stage cut its traffic by a quarter.
+  constexpr int MH = SLOT == 1 ? 2 : 1;
+  static_assert(MH * NC <= TMAXN, "the row blocks of a tile share one accumulator stage");
+  constexpr int NSTAGES = Ring<NC, MH>::stages;
+  constexpr uint32_t STAGE_B = Ring<NC, MH>::stage_bytes, OP_B = Ring<NC, MH>::op_bytes;
   __shared__ __align__(8) uint64_t s_bars[2 * TMAXSTAGES + 4];
   __shared__ uint32_t s_tmem_slot;
   __shared__ int s_block_done;
@@ -262,9 +267,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // stage s : [Xhi][Xlo][Ohi][Olo]   (X_TILE_BYTES, X_TILE_BYTES, OP_TILE_BYTES, OP_TILE_BYTES)
   auto st_xhi = [&](int s) { return smem_base + s * STAGE_B; };
-  auto st_xlo = [&](int s) { return smem_base + s * STAGE_B + X_TILE_BYTES; };
-  auto st_ohi = [&](int s) { return smem_base + s * STAGE_B + 2 * X_TILE_BYTES; };
-  auto st_olo = [&](int s) { return smem_base + s * STAGE_B + 2 * X_TILE_BYTES + OP_B; };
+  auto st_xlo = [&](int s) { return smem_base + s * STAGE_B + MH * X_TILE_BYTES; };
+  auto st_ohi = [&](int s) { return smem_base + s * STAGE_B + 2 * MH * X_TILE_BYTES; };
+  auto st_olo = [&](int s) { return smem_base + s * STAGE_B + 2 * MH * X_TILE_BYTES + OP_B; };
   const uint32_t bar_base = smem_u32(s_bars);
   auto bar_full = [&](int s) { return bar_base + 8 * s; };
   auto bar_empty = [&](int s) { return bar_base + 8 * (NSTAGES + s); };
@@ -305,7 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 #ifdef TC_EXP_SKIP_OLO   // timing experiment only (wrong results): is the kernel bound by operand delivery from L2?
   constexpr uint32_t stage_tx = 2 * X_TILE_BYTES + 1 * (uint32_t)NC * TBK * 4;
 #else
-  constexpr uint32_t stage_tx = 2 * X_TILE_BYTES + 2 * (uint32_t)NC * TBK * 4;
+  constexpr uint32_t stage_tx = 2 * MH * X_TILE_BYTES + 2 * (uint32_t)NC * TBK * 4;
 #endif
 
   if (warp == 0) {
@@ -336,10 +341,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           if (SLOT == 0) {
             tma_load_2d(st_xhi(stage), &tm_xhi, bar_full(stage), kx, row0 + p);
             tma_load_2d(st_xlo(stage), &tm_xlo, bar_full(stage), kx, row0 + p);
-          } else {                                           // 16 segments x 8 consecutive rows (windows) of each
+          } else {                                           // per row block: 16 segments x 8 consecutive rows (windows) of each
             const int sg = (int)(m_tile / prm.slots.jgroups), jg = (int)(m_tile - (int64_t)sg * prm.slots.jgroups);
-            tma_load_3d(st_xhi(stage), &tm_xhi, bar_full(stage), kx, 8 * jg, 16 * sg);
-            tma_load_3d(st_xlo(stage), &tm_xlo, bar_full(stage), kx, 8 * jg, 16 * sg);
+#pragma unroll
+            for (int h = 0; h < MH; ++h) {
+              tma_load_3d(st_xhi(stage) + h * X_TILE_BYTES, &tm_xhi, bar_full(stage), kx, 8 * jg, 16 * (MH * sg + h));
+              tma_load_3d(st_xlo(stage) + h * X_TILE_BYTES, &tm_xlo, bar_full(stage), kx, 8 * jg, 16 * (MH * sg + h));
+            }
           }
           if (!SCHED || rows == NC) {
             tma_load_2d(st_ohi(stage), &tm_ohi, bar_full(stage), kb * EPK, n0);
@@ -393,14 +401,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 #pragma unroll
             for (int k = 0; k < TBK / TUMMA_K; ++k) {
               const uint64_t adv = (uint64_t)((k * TUMMA_K * 4) >> 4);   // +32 B per k-step inside the swizzle row
-              if (kHalf) {
-                umma_f16(tmem_d, dxh + adv, doh + adv, idesc_e, (first && k == 0) ? 0u : 1u);
-                umma_f16(tmem_d, dxl + adv, doh + adv, idesc_e, 1u);
-                umma_f16(tmem_d, dxh + adv, dol + adv, idesc_e, 1u);
-              } else {
-                umma_tf32(tmem_d, dxh + adv, doh + adv, idesc_e, (first && k == 0) ? 0u : 1u);
-                umma_tf32(tmem_d, dxl + adv, doh + adv, idesc_e, 1u);
-                umma_tf32(tmem_d, dxh + adv, dol + adv, idesc_e, 1u);
+#pragma unroll
+              for (int h = 0; h < MH; ++h) {                              // row blocks sharing this operator tile
+                const uint64_t xa = adv + (uint64_t)((h * X_TILE_BYTES) >> 4);
+                const uint32_t td = tmem_d + (uint32_t)(h * NC);
+                if (kHalf) {
+                  umma_f16(td, dxh + xa, doh + adv, idesc_e, (first && k == 0) ? 0u : 1u);
+                  umma_f16(td, dxl + xa, doh + adv, idesc_e, 1u);
+                  umma_f16(td, dxh + xa, dol + adv, idesc_e, 1u);
+                } else {
+                  umma_tf32(td, dxh + xa, doh + adv, idesc_e, (first && k == 0) ? 0u : 1u);
+                  umma_tf32(td, dxl + xa, doh + adv, idesc_e, 1u);
+                  umma_tf32(td, dxh + xa, dol + adv, idesc_e, 1u);
+                }
               }
             }
             umma_commit(bar_empty(stage));                  // frees the smem slot when these MMAs retire
@@ -424,28 +437,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       const int64_t row = m_tile * TBM + q * 32 + lane;
       const int n0 = chunk * NC + half * H;
       const int n_sp = SCHED ? (s_sched_len[chunk] + prm.kb_per_split - 1) / prm.kb_per_split : n_splits;
-      float sum[H];
+      float sum[MH * H];
       for (int sp = 0; sp < n_sp; ++sp, ++it) {
         const int acc = (int)(it & 1u);
         mbar_wait(bar_tfull(acc), (it >> 1) & 1u);
         tc_fence_after();
         if (TFM == 0) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TMAXN + (uint32_t)(half * H);
 #pragma unroll
-          for (int c = 0; c + 16 <= H; c += 16) {
-            uint32_t r[16];
-            tmem_ld16(taddr + c, r);
-            tmem_ld_wait();
+          for (int h = 0; h < MH; ++h) {                         // row blocks of the tile: accumulator columns h * NC ..
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TMAXN + (uint32_t)(h * NC + half * H);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sum[c + j] = sp == 0 ? __uint_as_float(r[j]) : sum[c + j] + __uint_as_float(r[j]);
-          }
-          if (H % 16) {
-            constexpr int c = H - 8;
-            uint32_t r[8];
-            tmem_ld8(taddr + c, r);
-            tmem_ld_wait();
+            for (int c = 0; c + 16 <= H; c += 16) {
+              uint32_t r[16];
+              tmem_ld16(taddr + c, r);
+              tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sum[c + j] = sp == 0 ? __uint_as_float(r[j]) : sum[c + j] + __uint_as_float(r[j]);
+              for (int j = 0; j < 16; ++j)
+                sum[h * H + c + j] = sp == 0 ? __uint_as_float(r[j]) : sum[h * H + c + j] + __uint_as_float(r[j]);
+            }
+            if (H % 16) {
+              constexpr int c = H - 8;
+              uint32_t r[8];
+              tmem_ld8(taddr + c, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sum[h * H + c + j] = sp == 0 ? __uint_as_float(r[j]) : sum[h * H + c + j] + __uint_as_float(r[j]);
+            }
           }
         } else {
           // frame-major tile: accumulator column = t * 2B + bin_in_tile * 2 + {re, im}.  This warp takes HALF THE BINS of every
@@ -483,31 +501,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       // tile finished: undo the power-of-two operand scaling (exact), then |.|^2 + row max, or the raw complex values
       if (kHalf) {
 #pragma unroll
-        for (int c = 0; c < H; ++c) sum[c] *= prm.out_scale;
+        for (int c = 0; c < MH * H; ++c) sum[c] *= prm.out_scale;
       }
       if (SLOT > 0) {
         // ---- structured CQT: tile row rho = 8 * (segment within the group of 16) + (row within the group of 8)
         const SlotArgs& sl = prm.slots;
         const int rho = q * 32 + lane;
         const int sg = (int)(m_tile / sl.jgroups), jg = (int)(m_tile - (int64_t)sg * sl.jgroups);
-        const int64_t slot = 16 * (int64_t)sg + (rho >> 3);
+        const int64_t slot = 16 * (int64_t)sg * MH + (rho >> 3);     // of row block 0; block h: + 16 h
         const int j = 8 * jg + (rho & 7);
         const bool live = slot < sl.n_slots;
         if (SLOT == 1) {
-          const int len0 = live ? __ldg(sl.seg_len + slot) : 0;
           // decimator: row j holds outputs k = j * NC + n of the next octave; beyond the octave's length -> zeros (librosa
           // fixes the length to ceil(n / 2), and the next stage must see a zero-extended signal)
-          const int valid = halved_len(len0, sl.stage_out);
-          if (live) {
-            __half* hi = sl.out_hi + sl.out_base + slot * sl.out_stride + (int64_t)j * NC + half * H;
-            __half* lo = sl.out_lo + sl.out_base + slot * sl.out_stride + (int64_t)j * NC + half * H;
+#pragma unroll
+          for (int h = 0; h < MH; ++h) {
+            const int64_t slot_h = slot + 16 * h;
+            if (slot_h >= sl.n_slots) continue;
+            const int valid = halved_len(__ldg(sl.seg_len + slot_h), sl.stage_out);
+            __half* hi = sl.out_hi + sl.out_base + slot_h * sl.out_stride + (int64_t)j * NC + half * H;
+            __half* lo = sl.out_lo + sl.out_base + slot_h * sl.out_stride + (int64_t)j * NC + half * H;
             const int k0 = j * NC + half * H;
 #pragma unroll
             for (int c = 0; c < H; c += 8) {
               __align__(16) __half h8[8], l8[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
-                const float v = (k0 + c + u < valid) ? sum[c + u] * sl.plane_scale : 0.f;
+                const float v = (k0 + c + u < valid) ? sum[h * H + c + u] * sl.plane_scale : 0.f;
                 h8[u] = __float2half_rn(v);
                 l8[u] = __float2half_rn(v - __half2float(h8[u]));
               }
@@ -853,6 +873,13 @@ static int encode_3d(CUtensorMap* tm, const void* base, uint64_t k_extent, uint6
   return GTC_OK;
 }
 
+// function attributes are per device: called by gtc_scqt_plan_create on the plan's device
+int tc_slots_init() {
+  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128, false, true, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<32, false, true, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+  return GTC_OK;
+}
+
 int launch_gemm_tc_slots(const PlanImpl& p, const __half* x_hi, const __half* x_lo, int64_t x_first, int64_t x_stride,
                          int64_t row_step, int rows_per_slot, const SlotArgs& slots, cudaStream_t st) {
   GTC_REQUIRE(p.tmap_op_hi != nullptr && p.elem_bytes == 2 && p.parts == 1, GTC_E_ARG, "slotted GEMM needs an fp16x2 plan with one part");
@@ -878,16 +905,10 @@ int launch_gemm_tc_slots(const PlanImpl& p, const __half* x_hi, const __half* x_
   prm.parts = 1;
   prm.slots = slots;
   prm.slots.jgroups = rows_per_slot / 8;
-  prm.m_tiles = ceil_div(slots.n_slots, 16) * prm.slots.jgroups;
+  prm.m_tiles = ceil_div(slots.n_slots, slots.slot_mode == 1 ? 32 : 16) * prm.slots.jgroups;   // the decimator tile is two row blocks
   const unsigned grid = (unsigned)(prm.m_tiles < p.sm_count ? prm.m_tiles : p.sm_count);
   const CUtensorMap& tm_ohi = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_hi);
   const CUtensorMap& tm_olo = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_lo);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128, false, true, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<32, false, true, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    attr_set = true;
-  }
   if (slots.slot_mode == 1)
     gemm_tc_kernel<128, false, true, 0, 1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
   else

@@ -600,7 +600,8 @@ extern "C" int gtc_scqt_plan_create(gtc_splan** out, int device, int n_octaves, 
         if (m >= 0 && m < n_taps) op[(size_t)n * p.dec_k + i] = h_taps[m];
       }
     gtc_plan* sub = nullptr;
-    int rc = gtc_cqt_plan_create(&sub, device, p.dec_k, p.dec_k, 64, 1, op.data(), GTC_GEMM_TCGEN05_FP16X2);
+    int rc = tc_slots_init();
+    if (rc == GTC_OK) rc = gtc_cqt_plan_create(&sub, device, p.dec_k, p.dec_k, 64, 1, op.data(), GTC_GEMM_TCGEN05_FP16X2);
     p.dec_plan = sub;
     for (int i = 0; i < n_octaves && rc == GTC_OK; ++i) {
       std::vector<float> f((size_t)32 * n_fft, 0.f);

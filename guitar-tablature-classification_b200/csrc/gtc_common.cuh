@@ -247,6 +247,7 @@ int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int6
 // structured CQT: GEMM of slotted rows (3-D tensor maps over the hi/lo planes) against plan `p`'s operator
 int launch_gemm_tc_slots(const PlanImpl& p, const __half* x_hi, const __half* x_lo, int64_t x_first, int64_t x_stride,
                          int64_t row_step, int rows_per_slot, const SlotArgs& slots, cudaStream_t st);
+int tc_slots_init();
 int tc_plan_init(PlanImpl& p, const uint8_t* h_nz /* [n_pad / grp_rows][k_blocks] non-zero flags, or null */, int kb_per_split);
 int tc_pick_plain_width(int n_out);                       // tile width of the plain row order
 bool tc_has_frame_major_kernel(int nc, int n_frames);     // is gemm_tc_kernel instantiated for this frame-major tile?
