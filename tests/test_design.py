@@ -76,3 +76,31 @@ def test_structured_tables_reproduce_oracle_cqt(kw, n):
     V = emulate_structured(x, filters, n_fft, taps, r.hop_length, r.n_bins)
     assert V.shape == C.shape
     assert np.abs(V - C).max() < 3e-6 * np.abs(C).max()
+
+
+def test_operator_zero_structure_at_mma_granularity():
+    """The numbers DESIGN.md 3.1 quotes for the zero-skipping schedule of the tensor-core engine: fill of the segment
+    operator per (N tile of 24 bins) x (k-block of 32 samples) x (frame), in the library's frame-major tile order."""
+    from gtc_b200.cqt_design import CqtRecipe, get_operator
+    A = get_operator(CqtRecipe())
+    T, NB = 5, 96
+    nz = (A.reshape(T, NB, 2, 4410) != 0)
+    assert abs(nz.mean() - 0.634) < 0.005
+
+    def kblocks(mask):                                   # two audio rows of 2205 samples, each padded to 69 k-blocks of 32
+        out = []
+        for p in range(2):
+            m = np.zeros(2208, bool)
+            m[:2205] = mask[p * 2205:(p + 1) * 2205]
+            out.append(m.reshape(69, 32).any(1))
+        return np.concatenate(out)
+
+    fill = []
+    for tile in range(4):                                # library tile j = bins 24j .. 24j+23 (tile 3 = the two top octaves)
+        bins = slice(24 * tile, 24 * tile + 24)
+        fill.append(np.mean([kblocks(nz[t, bins].any(axis=(0, 1))).mean() for t in range(T)]))
+    assert fill[0] == 1.0 and fill[1] == 1.0             # low octaves: filters longer than the segment
+    assert abs(fill[2] - 0.635) < 0.01 and abs(fill[3] - 0.139) < 0.01
+    assert abs(np.mean(fill) - 0.694) < 0.01             # 31 % of the tensor work multiplied zeros
+    # whole-k-block skipping alone would reach far less: the union over a tile's five frames covers most of the segment
+    assert kblocks(nz[:, 72:96].any(axis=(0, 1, 2))).mean() > 0.69
