@@ -252,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // MH: 128-row blocks that share one operator tile.  The decimator is bound by L2 -> SM operand delivery and every tile uses
   // the SAME Toeplitz operator: two row blocks (32 segments x 8 rows) per operator stage cut its traffic by a quarter.
-  constexpr int MH = SLOT == 1 ? 2 : 1;
+  constexpr int MH = SLOT > 0 ? 2 : 1;
   static_assert(MH * NC <= TMAXN, "the row blocks of a tile share one accumulator stage");
   constexpr int NSTAGES = Ring<NC, MH>::stages;
   constexpr uint32_t STAGE_B = Ring<NC, MH>::stage_bytes, OP_B = Ring<NC, MH>::op_bytes;
@@ -538,22 +538,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         } else {
           // response: row j = frame t of the segment, columns = (bin, {re, im}) of the octave's filters
           const int t = j;
-          const bool valid = live && t < __ldg(sl.seg_frames + slot);      // frames librosa keeps (precomputed: 7 divisions)
-          float mx = 0.f;
 #pragma unroll
-          for (int c = 0; c < H; c += 2) {
-            const int b = (half * H + c) >> 1;
-            const float m = valid ? sum[c] * sum[c] + sum[c + 1] * sum[c + 1] : 0.f;
-            if (live && t < sl.t_max && b < sl.bin_cnt) {
-              sl.out[(slot * sl.n_bins + sl.bin_lo + b) * sl.t_max + t] = m;
-              mx = fmaxf(mx, m);
+          for (int h = 0; h < MH; ++h) {
+            const int64_t slot_h = slot + 16 * h;
+            const bool live_h = slot_h < sl.n_slots;
+            const bool valid = live_h && t < __ldg(sl.seg_frames + slot_h);      // frames librosa keeps (precomputed: 7 divisions)
+            float mx = 0.f;
+#pragma unroll
+            for (int c = 0; c < H; c += 2) {
+              const int b = (half * H + c) >> 1;
+              const float m = valid ? sum[h * H + c] * sum[h * H + c] + sum[h * H + c + 1] * sum[h * H + c + 1] : 0.f;
+              if (live_h && t < sl.t_max && b < sl.bin_cnt) {
+                sl.out[(slot_h * sl.n_bins + sl.bin_lo + b) * sl.t_max + t] = m;
+                mx = fmaxf(mx, m);
+              }
             }
+            // the 8 lanes of a segment's row group share one atomic
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+            if ((rho & 7) == 0 && live_h && mx > 0.f) atomicMax(reinterpret_cast<int*>(sl.segmax + slot_h), __float_as_int(mx));
           }
-          // the 8 lanes of a segment's row group share one atomic
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-          if ((rho & 7) == 0 && live && mx > 0.f) atomicMax(reinterpret_cast<int*>(sl.segmax + slot), __float_as_int(mx));
         }
       } else if (kComplex) {
         if (TFM == 0) {
@@ -905,7 +910,7 @@ int launch_gemm_tc_slots(const PlanImpl& p, const __half* x_hi, const __half* x_
   prm.parts = 1;
   prm.slots = slots;
   prm.slots.jgroups = rows_per_slot / 8;
-  prm.m_tiles = ceil_div(slots.n_slots, slots.slot_mode == 1 ? 32 : 16) * prm.slots.jgroups;   // the decimator tile is two row blocks
+  prm.m_tiles = ceil_div(slots.n_slots, 32) * prm.slots.jgroups;   // a slotted tile is two row blocks of 16 segments x 8 rows
   const unsigned grid = (unsigned)(prm.m_tiles < p.sm_count ? prm.m_tiles : p.sm_count);
   const CUtensorMap& tm_ohi = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_hi);
   const CUtensorMap& tm_olo = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_lo);
