@@ -345,8 +345,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             const int sg = (int)(m_tile / prm.slots.jgroups), jg = (int)(m_tile - (int64_t)sg * prm.slots.jgroups);
 #pragma unroll
             for (int h = 0; h < MH; ++h) {
-              tma_load_3d(st_xhi(stage) + h * X_TILE_BYTES, &tm_xhi, bar_full(stage), kx, 8 * jg, 16 * (MH * sg + h));
-              tma_load_3d(st_xlo(stage) + h * X_TILE_BYTES, &tm_xlo, bar_full(stage), kx, 8 * jg, 16 * (MH * sg + h));
+              const int bl = prm.slots.box_log2;
+              tma_load_3d(st_xhi(stage) + h * X_TILE_BYTES, &tm_xhi, bar_full(stage), kx, jg << bl, (MH * sg + h) << (7 - bl));
+              tma_load_3d(st_xlo(stage) + h * X_TILE_BYTES, &tm_xlo, bar_full(stage), kx, jg << bl, (MH * sg + h) << (7 - bl));
             }
           }
           if (!SCHED || rows == NC) {
@@ -508,15 +509,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         const SlotArgs& sl = prm.slots;
         const int rho = q * 32 + lane;
         const int sg = (int)(m_tile / sl.jgroups), jg = (int)(m_tile - (int64_t)sg * sl.jgroups);
-        const int64_t slot = 16 * (int64_t)sg * MH + (rho >> 3);     // of row block 0; block h: + 16 h
-        const int j = 8 * jg + (rho & 7);
+        const int bl = sl.box_log2, spb = 128 >> bl;                   // segments per row block
+        const int64_t slot = (int64_t)sg * MH * spb + (rho >> bl);     // of row block 0; block h: + spb * h
+        const int j = (jg << bl) + (rho & ((1 << bl) - 1));
         const bool live = slot < sl.n_slots;
         if (SLOT == 1) {
           // decimator: row j holds outputs k = j * NC + n of the next octave; beyond the octave's length -> zeros (librosa
           // fixes the length to ceil(n / 2), and the next stage must see a zero-extended signal)
 #pragma unroll
           for (int h = 0; h < MH; ++h) {
-            const int64_t slot_h = slot + 16 * h;
+            const int64_t slot_h = slot + spb * h;
             if (slot_h >= sl.n_slots) continue;
             const int valid = halved_len(__ldg(sl.seg_len + slot_h), sl.stage_out);
             __half* hi = sl.out_hi + sl.out_base + slot_h * sl.out_stride + (int64_t)j * NC + half * H;
@@ -540,7 +542,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           const int t = j;
 #pragma unroll
           for (int h = 0; h < MH; ++h) {
-            const int64_t slot_h = slot + 16 * h;
+            const int64_t slot_h = slot + spb * h;
             const bool live_h = slot_h < sl.n_slots;
             const bool valid = live_h && t < __ldg(sl.seg_frames + slot_h);      // frames librosa keeps (precomputed: 7 divisions)
             float mx = 0.f;
@@ -553,11 +555,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                 mx = fmaxf(mx, m);
               }
             }
-            // the 8 lanes of a segment's row group share one atomic
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-            if ((rho & 7) == 0 && live_h && mx > 0.f) atomicMax(reinterpret_cast<int*>(sl.segmax + slot_h), __float_as_int(mx));
+            // the lanes of a segment's row group share one atomic
+            for (int d = 1; d < (1 << bl); d <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            if ((rho & ((1 << bl) - 1)) == 0 && live_h && mx > 0.f) atomicMax(reinterpret_cast<int*>(sl.segmax + slot_h), __float_as_int(mx));
           }
         }
       } else if (kComplex) {
@@ -864,12 +864,12 @@ int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int6
 // ---- structured CQT: slotted rows (SlotArgs).  3-D map over one fp16 plane: (sample within the window, row within the
 // segment, segment); rows overlap (row stride < window length), box = one k-block x 8 rows x 16 segments = a 128-row tile.
 static int encode_3d(CUtensorMap* tm, const void* base, uint64_t k_extent, uint64_t rows, uint64_t slots, uint64_t row_step,
-                     uint64_t slot_stride) {
+                     uint64_t slot_stride, int box_log2) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return GTC_E_CUDA;
   cuuint64_t gdim[3] = {k_extent, rows, slots};
   cuuint64_t gstr[2] = {row_step * 2, slot_stride * 2};
-  cuuint32_t box[3] = {(cuuint32_t)(TKB_BYTES / 2), 8, 16};
+  cuuint32_t box[3] = {(cuuint32_t)(TKB_BYTES / 2), (cuuint32_t)(1 << box_log2), (cuuint32_t)(128 >> box_log2)};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   TKB_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : TKB_BYTES == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
@@ -891,13 +891,14 @@ int launch_gemm_tc_slots(const PlanImpl& p, const __half* x_hi, const __half* x_
   GTC_REQUIRE(p.bins_per_tile == 0 && p.n_out <= p.nc, GTC_E_ARG, "slotted GEMM: the operator must be one plain N tile");
   GTC_REQUIRE((slots.slot_mode == 1 && p.nc == 128) || (slots.slot_mode == 2 && p.nc == 32), GTC_E_UNSUP,
               "slotted GEMM: no kernel for mode %d with tile width %d", slots.slot_mode, p.nc);
-  GTC_REQUIRE(rows_per_slot > 0 && rows_per_slot % 8 == 0 && slots.n_slots > 0, GTC_E_ARG, "slotted GEMM: bad geometry");
+  GTC_REQUIRE(rows_per_slot > 0 && rows_per_slot % 2 == 0 && slots.n_slots > 0, GTC_E_ARG, "slotted GEMM: bad geometry");
+  const int box_log2 = rows_per_slot % 8 == 0 ? 3 : rows_per_slot % 4 == 0 ? 2 : 1;     // rows of a segment per TMA box
   GTC_REQUIRE(((x_first * 2) & 15) == 0 && ((row_step * 2) & 15) == 0 && ((x_stride * 2) & 15) == 0, GTC_E_ARG,
               "slotted GEMM: windows must start on 16-byte boundaries");
   CUtensorMap tm_xhi, tm_xlo;
-  int rc = encode_3d(&tm_xhi, x_hi + x_first, (uint64_t)p.kp, (uint64_t)rows_per_slot, (uint64_t)slots.n_slots, (uint64_t)row_step, (uint64_t)x_stride);
+  int rc = encode_3d(&tm_xhi, x_hi + x_first, (uint64_t)p.kp, (uint64_t)rows_per_slot, (uint64_t)slots.n_slots, (uint64_t)row_step, (uint64_t)x_stride, box_log2);
   if (rc != GTC_OK) return rc;
-  rc = encode_3d(&tm_xlo, x_lo + x_first, (uint64_t)p.kp, (uint64_t)rows_per_slot, (uint64_t)slots.n_slots, (uint64_t)row_step, (uint64_t)x_stride);
+  rc = encode_3d(&tm_xlo, x_lo + x_first, (uint64_t)p.kp, (uint64_t)rows_per_slot, (uint64_t)slots.n_slots, (uint64_t)row_step, (uint64_t)x_stride, box_log2);
   if (rc != GTC_OK) return rc;
   TcParams prm;
   memset(&prm, 0, sizeof(prm));
@@ -909,8 +910,9 @@ int launch_gemm_tc_slots(const PlanImpl& p, const __half* x_hi, const __half* x_
   prm.out_scale = p.out_scale;
   prm.parts = 1;
   prm.slots = slots;
-  prm.slots.jgroups = rows_per_slot / 8;
-  prm.m_tiles = ceil_div(slots.n_slots, 32) * prm.slots.jgroups;   // a slotted tile is two row blocks of 16 segments x 8 rows
+  prm.slots.box_log2 = box_log2;
+  prm.slots.jgroups = rows_per_slot >> box_log2;
+  prm.m_tiles = ceil_div(slots.n_slots, 2 * (128 >> box_log2)) * prm.slots.jgroups;   // a slotted tile is two 128-row blocks
   const unsigned grid = (unsigned)(prm.m_tiles < p.sm_count ? prm.m_tiles : p.sm_count);
   const CUtensorMap& tm_ohi = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_hi);
   const CUtensorMap& tm_olo = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_lo);

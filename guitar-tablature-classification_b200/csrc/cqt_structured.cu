@@ -271,7 +271,7 @@ constexpr int kPlaneFront = 512;          // zero samples in front of segment 0 
 constexpr float kPlaneScale = 256.f;      // == the fp16x2 engine's x_scale (cqt_api.cu)
 
 struct TcGeom {
-  int64_t S[kMaxOctaves];                 // samples per segment slot of octave i (multiple of 1024, >= len_i + guard)
+  int64_t S[kMaxOctaves];                 // samples per segment slot of octave i (multiple of 256, >= len_i + guard)
   int64_t plane_elems[kMaxOctaves];       // halves per plane
   size_t off_hi[kMaxOctaves], off_lo[kMaxOctaves];
   int t_pad;                              // frames per segment, padded to 8
@@ -283,7 +283,7 @@ static void tc_geometry(const SPlanImpl& p, int64_t n_seg, int64_t max_len, TcGe
   int64_t len = max_len;
   const int64_t guard = p.dec_left + 8 > p.n_fft / 2 ? p.dec_left + 8 : p.n_fft / 2;
   for (int i = 0; i < p.n_oct; ++i) {
-    g.S[i] = round_up(len + guard, 1024);
+    g.S[i] = round_up(len + guard, 256);                  // whole pairs of 128-output rows (the smallest TMA box is 64 segments x 2 rows)
     len = (len + 1) / 2;
   }
   for (int i = 0; i < p.n_oct; ++i) {

@@ -174,12 +174,13 @@ struct OpLayout {
 // ---- "slotted" M operand of the tensor-core engine (structured CQT, cqt_structured.cu).  The rows of the GEMM are windows
 // of per-segment signals stored as fp16 hi/lo planes: segment s owns `stride` samples starting at base + s * stride, row j
 // of a segment is the window starting at j * row_step samples (windows overlap: the TMA tensor map simply has a row stride
-// smaller than the row length).  A 128-row tile is 16 segments x 8 consecutive rows (3-D TMA box), so short and ragged
-// segments waste at most 7 rows each.  slot_mode: 1 = 2:1 decimator (output: the next octave's hi/lo planes, samples
+// smaller than the row length).  A 128-row block is 16 segments x 8 consecutive rows (3-D TMA box) -- or 32 x 4 / 64 x 2 for
+// the short low octaves -- so short and ragged segments waste at most 7 (3, 1) rows each.  slot_mode: 1 = 2:1 decimator (output: the next octave's hi/lo planes, samples
 // beyond the segment's length zeroed), 2 = octave response (output: |C|^2 into [seg][bin][t] + the segment maximum).
 struct SlotArgs {
   int slot_mode;            // 0 = off
-  int jgroups;              // groups of 8 rows per segment
+  int jgroups;              // row groups per segment
+  int box_log2;             // a 128-row block is (128 >> box_log2) segments x (1 << box_log2) consecutive rows: 3 (16 x 8), 2 (32 x 4) or 1 (64 x 2)
   int64_t n_slots;          // segments
   // mode 1
   __half* out_hi;
