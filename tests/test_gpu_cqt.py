@@ -172,3 +172,39 @@ def test_fused_finish_option_is_bit_identical(recipe, lib, clips):
             c = run_gpu(p, cl)                                                    # counters are left clean for the next call
             assert np.array_equal(a, b) and np.array_equal(b, c)
         p.close()
+
+
+def test_zero_skipping_schedule_equals_dense_loops(recipe, lib, clips, monkeypatch):
+    """The tensor-core engine multiplies a k-block only with the frames whose operator rows are non-zero on it (the plan's
+    schedule, cqt_gemm_tc.cu); GTC_TC_DENSE=1 at plan creation restores the dense loops.  Same products, K splits cut at
+    other places: complex outputs agree to fp32 rounding, dB features to 1e-3 dB away from the cut."""
+    from gtc_b200 import ops
+    big = clips + [make_test_audio(SR * 3, seed=190 + i) for i in range(40)]      # several row blocks, rotated tile order
+    p_s = ops.CqtPlan(recipe)
+    monkeypatch.setenv("GTC_TC_DENSE", "1")
+    p_d = ops.CqtPlan(recipe)
+    monkeypatch.delenv("GTC_TC_DENSE")
+    a, b = run_gpu(p_s, big, complex_out=True), run_gpu(p_d, big, complex_out=True)
+    peak = np.abs(b).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(a - b) / np.maximum(peak, 1e-20)).max() < 3e-6
+    da, db = run_gpu(p_s, big), run_gpu(p_d, big)
+    both = (da > -59.9) & (db > -59.9)
+    assert np.abs(da - db)[both].max() < 1e-3 and ((da == -120) != (db == -120)).mean() < 1e-4
+    p_s.close(); p_d.close()
+
+
+def test_plan_from_a_caller_supplied_operator(recipe, lib, clips):
+    """The pinning hook (scripts/pin_with_librosa.py): CqtPlan(operator=A) evaluates the matrix the caller hands over -- e.g.
+    one measured from the real librosa.cqt -- instead of the designed one.  The designed matrix gives the default plan's
+    bits; a scaled copy scales the complex output."""
+    from gtc_b200 import ops
+    from gtc_b200.cqt_design import get_operator
+    A = np.array(get_operator(recipe), dtype=np.float32)
+    p0, p1, p2 = ops.CqtPlan(recipe), ops.CqtPlan(recipe, operator=A), ops.CqtPlan(recipe, operator=0.5 * A)
+    c0, c1, c2 = (run_gpu(p, clips, complex_out=True) for p in (p0, p1, p2))
+    assert np.array_equal(c0, c1)
+    assert np.abs(c2 - 0.5 * c0).max() <= 1e-6 * np.abs(c0).max()
+    with pytest.raises(Exception):
+        ops.CqtPlan(recipe, operator=A[:, :100])
+    for p in (p0, p1, p2):
+        p.close()
