@@ -33,7 +33,9 @@ for eng in engines:
         assert torch.equal(db, db3)
     torch.cuda.synchronize(); plan.close(); done.append(f"cqt engine {eng}: {n_seg} segments")
 
-sp = ops.StructuredCqtPlan(r)
+if no_tma:
+    os.environ["GTC_SCQT_SIMT"] = "1"            # structured CQT on its fp32 CUDA-core kernels (no TMA / tcgen05 under racecheck)
+sp = ops.StructuredCqtPlan(r)                     # default: decimator + response GEMMs on the slotted tcgen05 kernels
 starts = torch.tensor([0, 2205, int(lens[0]), int(lens[0]) + 100], dtype=torch.int64, device=dev)
 valid = torch.tensor([4410, 4410, 3000, 1234], dtype=torch.int32, device=dev)
 seglen = torch.tensor([4410, 4410, 4410, 4410], dtype=torch.int32, device=dev)
@@ -41,6 +43,16 @@ sdb = sp.segments_db(a_dev, starts, valid, seglen, 4410)
 scx = sp.segments_complex(pcm, starts, valid, seglen, 4410)
 half = sp.halve_rate(a_dev[:10001])
 torch.cuda.synchronize(); sp.close(); done.append("structured cqt + decimator")
+if not no_tma:
+    os.environ["GTC_TC_DENSE"] = "1"              # the dense loops of the tensor-core engine (default plans use the zero-skipping schedule)
+    plan = ops.CqtPlan(r)
+    co, so = plan.offsets(lens)
+    plan.segments_db(a_dev, torch.from_numpy(co).to(dev), torch.from_numpy(so).to(dev), int(so[-1]))
+    torch.cuda.synchronize(); plan.close(); del os.environ["GTC_TC_DENSE"]; done.append("dense tensor-core loops")
+    os.environ["GTC_SCQT_SIMT"] = "1"
+    sp = ops.StructuredCqtPlan(r)
+    sp.segments_db(a_dev, starts, valid, seglen, 4410)
+    torch.cuda.synchronize(); sp.close(); del os.environ["GTC_SCQT_SIMT"]; done.append("structured cqt, fp32 SIMT kernels")
 
 on, du, pi, eoff = synth.note_events([n / SR for n in lens], seed=3)
 plan = ops.CqtPlan(r, engine=_lib.GTC_GEMM_SIMT_FP32)
