@@ -84,3 +84,25 @@ def test_window_arithmetic():
     assert co.num_segments(661500, w, h) == 299
     assert co.num_segments(4409, w, h) == 0 and co.num_segments(4410, w, h) == 1
     assert co.window_params(44100) == (8820, 4410)
+
+
+def test_decimator_meets_the_published_soxr_hq_specification():
+    """Spec-level check of the restated 2:1 stage, independent of HOW its taps are computed: libsoxr's documented HQ quality is
+    20-bit precision (soxr.h: SOXR_HQ "20-bit"), linear phase, pass-band end 0.913 of the new Nyquist (1 - 0.05 / TO_3dB), stop-band
+    from the new Nyquist on; its DFT stage is designed for (20 + 1) x 6.02 = 126.4 dB.  The frequency response of the
+    table shared by the product and the oracle must show exactly that (it cannot tell WHICH Kaiser-class filter meets the
+    spec -- profiles/r02_tap_sensitivity.md bounds that freedom)."""
+    from gtc_b200 import cqt_design
+    h = co.soxr_hq_halfband_taps()
+    assert np.array_equal(h, cqt_design.decimator_taps())                     # one table for product and checker
+    assert len(h) % 4 == 1 and np.abs(h - h[::-1]).max() == 0.0              # linear phase, libsoxr's tap-count rule
+    n = 1 << 18
+    H = np.abs(np.fft.rfft(h, n))
+    f = np.arange(len(H)) / (n / 2)                                           # in units of the INPUT Nyquist
+    lin2db = 20 * np.log10(2.0)
+    passband_end = (1 - 0.05 / ((1.6e-6 * 20 * lin2db - 7.5e-4) * 20 * lin2db + 0.646)) / 2
+    assert abs(passband_end - 0.45682) < 1e-5
+    assert np.abs(20 * np.log10(H[f <= passband_end])).max() < 1e-5         # flat to 1e-5 dB over the pass-band
+    assert 20 * np.log10(H[f >= 0.5].max()) < -(20 + 1) * lin2db             # >= 126.4 dB from the new Nyquist on: no aliasing
+    assert abs(f[np.argmin(np.abs(H - 0.5))] - 0.47841) < 2e-4               # -6 dB at Fc = Fs - tr_bw
+    assert abs(H[0] - 1.0) < 1e-7
