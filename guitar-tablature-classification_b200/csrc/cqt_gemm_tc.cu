@@ -73,10 +73,9 @@ struct TcParams {
   SlotArgs slots;        // SLOT > 0 kernels: slotted rows of the structured CQT
   // zero-skipping schedule (null = every k-block against the whole N tile).  Entry = kb | g0 << 16 | ng << 24: multiply k-block
   // kb with the ng row groups starting at group g0 of the tile; the first entry of every K split covers the whole tile
-  // (it zero-initialises the accumulator stage).  Tiles are then ordered by passes over the N tiles, heaviest first.
+  // (it zero-initialises the accumulator stage).  The N tile index is then rotated by the CTA's iteration (tile_of).
   const uint32_t* sched;
   const int* sched_len;
-  const int* chunk_order;
   const CUtensorMap* op_maps;   // [n_groups][2] operator boxes of (g + 1) * grp_rows rows (hi, lo), device memory
   int sched_pitch, grp_rows, rotate;
 };
@@ -512,7 +511,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         const int bl = sl.box_log2, spb = 128 >> bl;                   // segments per row block
         const int64_t slot = (int64_t)sg * MH * spb + (rho >> bl);     // of row block 0; block h: + spb * h
         const int j = (jg << bl) + (rho & ((1 << bl) - 1));
-        const bool live = slot < sl.n_slots;
         if (SLOT == 1) {
           // decimator: row j holds outputs k = j * NC + n of the next octave; beyond the octave's length -> zeros (librosa
           // fixes the length to ceil(n / 2), and the next stage must see a zero-extended signal)
@@ -741,11 +739,10 @@ int tc_plan_init(PlanImpl& p, const uint8_t* h_nz, int kb_per_split) {
   //      around its frame, so the range is 1-2 frames wide in the top octaves and all of them in the low ones).
   const int n_chunks = (int)ceil_div(p.n_out, p.nc), n_grp = p.nc / p.grp_rows, nkb = p.k_total / p.kb_elems;
   const int exp_mode = getenv("GTC_TC_SCHED_MODE") ? atoi(getenv("GTC_TC_SCHED_MODE")) : 0;   // experiments: 1 = whole-tile entries, 2 = no rotation of the N tiles
-  p.sched_pass_order = (exp_mode & 2) ? 0 : 1;
+  p.sched_rotate = (exp_mode & 2) ? 0 : 1;
   if (n_grp < 2 || n_grp > 255 || nkb > 65535) return GTC_OK;
   std::vector<uint32_t> sched((size_t)n_chunks * nkb, 0);
-  std::vector<int> len(n_chunks, 0), order(n_chunks);
-  std::vector<long long> cost(n_chunks, 0);
+  std::vector<int> len(n_chunks, 0);
   long long work = 0;
   for (int c = 0; c < n_chunks; ++c) {
     int n = 0;
@@ -756,17 +753,12 @@ int tc_plan_init(PlanImpl& p, const uint8_t* h_nz, int kb_per_split) {
       if (g0 < 0) continue;                                         // nothing of this tile lives on this k-block
       if (n % kb_per_split == 0 || (exp_mode & 1)) { g0 = 0; g1 = n_grp - 1; }   // first entry of a K split: whole tile, zero-initialises
       sched[(size_t)c * nkb + n++] = (uint32_t)kb | ((uint32_t)g0 << 16) | ((uint32_t)(g1 - g0 + 1) << 24);
-      cost[c] += g1 - g0 + 1;
+      work += g1 - g0 + 1;
     }
     len[c] = n;
-    work += cost[c];
-    order[c] = c;
   }
   p.sched_fill = (float)work / (float)((long long)n_chunks * nkb * n_grp);
   if (p.sched_fill > 0.92f && !(exp_mode & 1)) return GTC_OK;                          // nothing worth skipping: keep the dense loops
-  for (int i = 0; i < n_chunks; ++i)                                 // passes by decreasing cost (stable)
-    for (int j = i + 1; j < n_chunks; ++j)
-      if (cost[order[j]] > cost[order[i]]) { int t = order[i]; order[i] = order[j]; order[j] = t; }
   std::vector<CUtensorMap> gm((size_t)2 * n_grp);
   for (int g = 0; g < n_grp; ++g) {
     rc = encode_2d(&gm[2 * g], p.d_op_hi, (uint64_t)p.n_pad, (uint64_t)p.k_total, (uint32_t)((g + 1) * p.grp_rows), p.elem_bytes);
@@ -777,8 +769,6 @@ int tc_plan_init(PlanImpl& p, const uint8_t* h_nz, int kb_per_split) {
   GTC_CUDA_CHECK(cudaMemcpy(p.d_sched, sched.data(), sched.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   GTC_CUDA_CHECK(cudaMalloc((void**)&p.d_sched_len, n_chunks * sizeof(int)));
   GTC_CUDA_CHECK(cudaMemcpy(p.d_sched_len, len.data(), n_chunks * sizeof(int), cudaMemcpyHostToDevice));
-  GTC_CUDA_CHECK(cudaMalloc((void**)&p.d_chunk_order, n_chunks * sizeof(int)));
-  GTC_CUDA_CHECK(cudaMemcpy(p.d_chunk_order, order.data(), n_chunks * sizeof(int), cudaMemcpyHostToDevice));
   GTC_CUDA_CHECK(cudaMalloc(&p.d_op_maps, gm.size() * sizeof(CUtensorMap)));
   GTC_CUDA_CHECK(cudaMemcpy(p.d_op_maps, gm.data(), gm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
   p.sched_pitch = nkb;
@@ -800,9 +790,8 @@ void tc_plan_free(PlanImpl& p) {
   p.tmap_op_hi = p.tmap_op_lo = nullptr;
   if (p.d_sched) cudaFree(p.d_sched);
   if (p.d_sched_len) cudaFree(p.d_sched_len);
-  if (p.d_chunk_order) cudaFree(p.d_chunk_order);
   if (p.d_op_maps) cudaFree(p.d_op_maps);
-  p.d_sched = nullptr; p.d_sched_len = nullptr; p.d_chunk_order = nullptr; p.d_op_maps = nullptr;
+  p.d_sched = nullptr; p.d_sched_len = nullptr; p.d_op_maps = nullptr;
 }
 
 int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int64_t n_rows_pad, int64_t n_rows_alloc,
@@ -830,7 +819,6 @@ int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int6
                          prm.n_chunks <= 16 && prm.n_chunks * p.sched_pitch <= 4096;
   prm.sched = use_sched ? p.d_sched : nullptr;
   prm.sched_len = p.d_sched_len;
-  prm.chunk_order = p.d_chunk_order;
   prm.op_maps = reinterpret_cast<const CUtensorMap*>(p.d_op_maps);
   prm.sched_pitch = p.sched_pitch;
   prm.grp_rows = p.grp_rows;
@@ -839,7 +827,7 @@ int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int6
   const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
   const CUtensorMap& tm_ohi = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_hi);
   const CUtensorMap& tm_olo = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_lo);
-  prm.rotate = use_sched && p.sched_pass_order && grid % (unsigned)prm.n_chunks == 0;
+  prm.rotate = use_sched && p.sched_rotate && grid % (unsigned)prm.n_chunks == 0;
   if (use_sched) {
     const bool cplx = d_cplx != nullptr;
     if (p.nc == 240 && p.n_frames == 5) {

@@ -230,10 +230,9 @@ struct PlanImpl {
   int sched_ksplit;        // k-blocks per accumulation split the schedule was built for (its first entry per split is dense)
   uint32_t* d_sched;       // [n_chunks][sched_pitch]  kb | g0 << 16 | ng << 24 ; null = dense
   int* d_sched_len;        // [n_chunks]
-  int* d_chunk_order;      // [n_chunks] N tiles by decreasing cost: tile T -> (chunk_order[T / m_tiles], T % m_tiles)
   void* d_op_maps;         // CUtensorMap[n_groups][2] in device memory: operator boxes of (g + 1) * grp_rows rows, hi / lo
   float sched_fill;        // scheduled tensor work / dense tensor work (1 = nothing to skip)
-  int sched_pass_order;    // 1: tiles in passes over the N tiles (heaviest first); 0: row-block major
+  int sched_rotate;        // 1: the N tile index is rotated by the CTA's iteration (balances tile types); 0: experiments
 };
 
 // launchers (each enqueues on `st`, returns a GTC_* code); xhi/xlo element type follows PlanImpl::elem_bytes
