@@ -51,6 +51,26 @@ struct Ring {
   static constexpr int fit = (int)((TC_SMEM_BYTES - 1024) / stage_bytes);
   static constexpr int stages = fit > TMAXSTAGES ? TMAXSTAGES : fit;
 };
+// RES kernels (decimator): the operator never travels again after the first load.  The banded Toeplitz operator of a 2:1 FIR,
+// Op[n][i] = h[2n + c - i], repeats itself from one k-block to the next shifted by `res_shift` = (elements per k-block) / 2 rows:
+//     Op[n][kb * EPK + e] = Master[n + res_shift * (nkb - 1 - kb)][e],      Master[r][e] = Op[r][(nkb - 1) * EPK + e] extended upwards
+// so ONE [kResRows][k-block] tile per hi/lo plane (2 x 32 KB at 64-byte k-blocks), loaded once per CTA, serves every k-block of
+// every tile: the B descriptor of k-block kb just starts res_shift * (nkb - 1 - kb) rows further down (a multiple of the 8-row
+// swizzle group, so the swizzle phase is unchanged).  The ring then carries X rows only.
+constexpr int kResRows = 512;
+constexpr uint32_t RES_MASTER_BYTES = 2u * kResRows * TKB_BYTES;              // hi + lo
+template <int MH>
+struct RingRes {
+  static constexpr uint32_t stage_bytes = 2 * MH * X_TILE_BYTES;
+  static constexpr uint32_t budget = 227u * 1024u - 1024u /*static smem + slack*/ - 1024u /*align*/ - RES_MASTER_BYTES;
+  static constexpr int fit = (int)(budget / stage_bytes);
+#ifdef TC_RES_STAGES                      // experiments: ring depth of the resident-operator kernels
+  static constexpr int stages = TC_RES_STAGES;
+#else
+  static constexpr int stages = fit > TMAXSTAGES ? TMAXSTAGES : fit;
+#endif
+  static constexpr uint32_t smem_bytes = RES_MASTER_BYTES + stages * stage_bytes + 1024;
+};
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 #ifndef TC_MAXNREG
@@ -78,6 +98,7 @@ struct TcParams {
   const int* sched_len;
   const CUtensorMap* op_maps;   // [n_groups][2] operator boxes of (g + 1) * grp_rows rows (hi, lo), device memory
   int sched_pitch, grp_rows, rotate;
+  int res_shift;         // RES kernels: operator rows by which consecutive k-blocks of the Toeplitz operator are shifted
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -173,6 +194,24 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&r)[8]) {
                : "r"(addr) : "memory");
 }
 
+// One round of the 8 x 8 transpose of 16-byte vectors among the 8 lanes of a group (xor butterfly): lane i, slot c  <->  lane c,
+// slot i after the rounds B = 4, 2, 1.  All register indices are compile-time.
+template <int B>
+__device__ __forceinline__ void xpose8_round(uint4 (&ch)[8], int i8) {
+  const bool up = (i8 & B) != 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (c & B) continue;
+    const uint4 send = up ? ch[c] : ch[c | B];
+    uint4 recv;
+    recv.x = __shfl_xor_sync(0xffffffffu, send.x, B);
+    recv.y = __shfl_xor_sync(0xffffffffu, send.y, B);
+    recv.z = __shfl_xor_sync(0xffffffffu, send.z, B);
+    recv.w = __shfl_xor_sync(0xffffffffu, send.w, B);
+    if (up) ch[c] = recv; else ch[c | B] = recv;
+  }
+}
+
 // dB finish of one completed 128-row block by the 8 epilogue warps of the CTA that completed it (see the call site).
 // Two rows x 4 vectors in flight per lane: the accumulation loop above it runs at the 168-register cap (10 warps = 3 on the
 // fullest SM sub-partition), more rows in flight -- or a non-inlined call -- push ptxas into spilling inside that loop.
@@ -239,7 +278,8 @@ __device__ __forceinline__ void fused_finish_block(const TcParams& prm, int64_t 
 // TFM > 0: frame-major tiles (OpLayout, gtc_common.cuh) of a TFM-frame recipe: NC = 2 * TFM * bins_per_tile; 0: plain rows.
 // SLOT > 0: the M operand is slotted (SlotArgs, gtc_common.cuh): 1 = decimator epilogue, 2 = response epilogue.
 // SCHED: multiply every k-block only with the row groups (frames) of the tile that are non-zero on it (TcParams::sched).
-template <int NC, bool kComplex, bool kHalf, int TFM, int SLOT = 0, bool SCHED = false>
+// RES: the (Toeplitz) operator is resident in shared memory as one master tile (see RingRes); SLOT == 1 only.
+template <int NC, bool kComplex, bool kHalf, int TFM, int SLOT = 0, bool SCHED = false, bool RES = false>
 __global__ void __maxnreg__(TC_MAXNREG)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo,
@@ -253,9 +293,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   // the SAME Toeplitz operator: two row blocks (32 segments x 8 rows) per operator stage cut its traffic by a quarter.
   constexpr int MH = SLOT > 0 ? 2 : 1;
   static_assert(MH * NC <= TMAXN, "the row blocks of a tile share one accumulator stage");
-  constexpr int NSTAGES = Ring<NC, MH>::stages;
-  constexpr uint32_t STAGE_B = Ring<NC, MH>::stage_bytes, OP_B = Ring<NC, MH>::op_bytes;
-  __shared__ __align__(8) uint64_t s_bars[2 * TMAXSTAGES + 4];
+  static_assert(!RES || (SLOT == 1 && !SCHED && kHalf && NC == TBM), "resident operator: the decimator's square fp16x2 tiles only");
+  constexpr int NSTAGES = RES ? RingRes<MH>::stages : Ring<NC, MH>::stages;
+  constexpr uint32_t STAGE_B = RES ? RingRes<MH>::stage_bytes : Ring<NC, MH>::stage_bytes, OP_B = Ring<NC, MH>::op_bytes;
+  __shared__ __align__(8) uint64_t s_bars[2 * TMAXSTAGES + 5];
   __shared__ uint32_t s_tmem_slot;
   __shared__ int s_block_done;
   // the schedule lives in shared memory: the producer and the MMA issuer read one entry per k-block on their critical path,
@@ -263,8 +304,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   constexpr int kSchedMax = 4096;
   __shared__ uint32_t s_sched[SCHED ? kSchedMax : 1];
   __shared__ int s_sched_len[SCHED ? 16 : 1];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  // stage s : [Xhi][Xlo][Ohi][Olo]   (X_TILE_BYTES, X_TILE_BYTES, OP_TILE_BYTES, OP_TILE_BYTES)
+  const uint32_t smem_al = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // RES: [master hi][master lo] in front of the ring
+  const uint32_t res_hi = smem_al, res_lo = smem_al + RES_MASTER_BYTES / 2;
+  const uint32_t smem_base = smem_al + (RES ? RES_MASTER_BYTES : 0u);
+  // stage s : [Xhi][Xlo][Ohi][Olo]   (X_TILE_BYTES, X_TILE_BYTES, OP_TILE_BYTES, OP_TILE_BYTES); RES: [Xhi][Xlo] only
   auto st_xhi = [&](int s) { return smem_base + s * STAGE_B; };
   auto st_xlo = [&](int s) { return smem_base + s * STAGE_B + MH * X_TILE_BYTES; };
   auto st_ohi = [&](int s) { return smem_base + s * STAGE_B + 2 * MH * X_TILE_BYTES; };
@@ -274,6 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   auto bar_empty = [&](int s) { return bar_base + 8 * (NSTAGES + s); };
   auto bar_tfull = [&](int a) { return bar_base + 8 * (2 * NSTAGES + a); };
   auto bar_tempty = [&](int a) { return bar_base + 8 * (2 * NSTAGES + 2 + a); };
+  const uint32_t bar_res = bar_base + 8 * (2 * NSTAGES + 4);       // RES: the master tile has landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -281,6 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), TC_EPI_WARPS); }
+    mbar_init(bar_res, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&s_tmem_slot), 512);
@@ -309,7 +355,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 #ifdef TC_EXP_SKIP_OLO   // timing experiment only (wrong results): is the kernel bound by operand delivery from L2?
   constexpr uint32_t stage_tx = 2 * X_TILE_BYTES + 1 * (uint32_t)NC * TBK * 4;
 #else
-  constexpr uint32_t stage_tx = 2 * MH * X_TILE_BYTES + 2 * (uint32_t)NC * TBK * 4;
+  constexpr uint32_t stage_tx = 2 * MH * X_TILE_BYTES + (RES ? 0u : 2 * (uint32_t)NC * TBK * 4);
 #endif
 
   if (warp == 0) {
@@ -319,6 +365,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_xlo)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_ohi)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_olo)) : "memory");
+      if (RES) {
+        // master tile: 128-row boxes of the operator's LAST k-block, of the k-block 128 / shift further left, ... and, once the
+        // k-blocks run out, of k-block 0 from row r - shift * (nkb - 1) on (rows past the operator are zero-filled by the TMA)
+        const int need = TBM + prm.res_shift * (nkb - 1);
+        mbar_expect_tx(bar_res, (uint32_t)((need + TBM - 1) / TBM) * 2u * TBM * TKB_BYTES);
+        for (int r = 0; r < need; r += TBM) {
+          int kb = nkb - 1 - r / prm.res_shift, n_start = 0;
+          if (kb < 0) { n_start = r - prm.res_shift * (nkb - 1); kb = 0; }
+          tma_load_2d(res_hi + (uint32_t)r * TKB_BYTES, &tm_ohi, bar_res, kb * EPK, n_start);
+          tma_load_2d(res_lo + (uint32_t)r * TKB_BYTES, &tm_olo, bar_res, kb * EPK, n_start);
+        }
+      }
       int stage = 0; uint32_t phase = 0;
       int iter = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
@@ -334,6 +392,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             kb = (int)(w & 0xffffu); g0 = (int)((w >> 16) & 0xffu); rows = (int)(w >> 24) * prm.grp_rows;
           }
           mbar_wait(bar_empty(stage), phase ^ 1);
+#ifdef TC_EXP_NO_XLOAD      // timing experiment only: no operand traffic at all in the resident kernels
+          if (RES) { mbar_arrive(bar_full(stage)); if (++stage == NSTAGES) { stage = 0; phase ^= 1; } continue; }
+#endif
           mbar_expect_tx(bar_full(stage), rows == NC ? stage_tx : 2 * X_TILE_BYTES + 2 * (uint32_t)rows * TBK * 4);
           const int p = kb / prm.kb_per_part;
           const int kx = (kb - p * prm.kb_per_part) * EPK;
@@ -349,7 +410,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
               tma_load_3d(st_xlo(stage) + h * X_TILE_BYTES, &tm_xlo, bar_full(stage), kx, jg << bl, (MH * sg + h) << (7 - bl));
             }
           }
-          if (!SCHED || rows == NC) {
+          if (RES) {
+            // nothing: the operator is resident
+          } else if (!SCHED || rows == NC) {
             tma_load_2d(st_ohi(stage), &tm_ohi, bar_full(stage), kb * EPK, n0);
 #ifndef TC_EXP_SKIP_OLO
             tma_load_2d(st_olo(stage), &tm_olo, bar_full(stage), kb * EPK, n0);
@@ -371,18 +434,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       int stage = 0; uint32_t phase = 0;
       uint32_t it = 0;                                       // accumulator-stage use counter (one per K split)
       int iter = 0;
+      if (RES) { mbar_wait(bar_res, 0); tc_fence_after(); }
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
         int64_t m_tile; int chunk;
         tile_of(tile, iter, m_tile, chunk);
         const int n_ent = SCHED ? s_sched_len[chunk] : nkb;
-        const int n_sp = SCHED ? (n_ent + prm.kb_per_split - 1) / prm.kb_per_split : n_splits;
+        const int n_sp = SLOT == 1 ? 1 : SCHED ? (n_ent + prm.kb_per_split - 1) / prm.kb_per_split : n_splits;   // decimator: see its epilogue
         int kb = 0;                                          // entry index
         for (int sp = 0; sp < n_sp; ++sp, ++it) {
           const int acc = (int)(it & 1u);
           mbar_wait(bar_tempty(acc), ((it >> 1) & 1u) ^ 1u); // epilogue drained this accumulator stage
           tc_fence_after();
           uint32_t tmem_d = tmem_base + (uint32_t)acc * TMAXN;
-          const int kb_end = min(n_ent, kb + prm.kb_per_split);
+          const int kb_end = SLOT == 1 ? n_ent : min(n_ent, kb + prm.kb_per_split);
           for (int first = 1; kb < kb_end; ++kb, first = 0) {
             uint32_t idesc_e = idesc;
             tmem_d = tmem_base + (uint32_t)acc * TMAXN;
@@ -397,7 +461,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             mbar_wait(bar_full(stage), phase);
             tc_fence_after();
             const uint64_t dxh = make_swizzle_desc(st_xhi(stage)), dxl = make_swizzle_desc(st_xlo(stage));
-            const uint64_t doh = make_swizzle_desc(st_ohi(stage)), dol = make_swizzle_desc(st_olo(stage));
+            const uint32_t res_at = RES ? (uint32_t)(prm.res_shift * (nkb - 1 - kb)) * TKB_BYTES : 0u;   // kb == the k-block (no schedule)
+            const uint64_t doh = make_swizzle_desc(RES ? res_hi + res_at : st_ohi(stage));
+            const uint64_t dol = make_swizzle_desc(RES ? res_lo + res_at : st_olo(stage));
+#ifdef TC_EXP_NO_MMA        // timing experiment only
+            if (!RES)
+#endif
 #pragma unroll
             for (int k = 0; k < TBK / TUMMA_K; ++k) {
               const uint64_t adv = (uint64_t)((k * TUMMA_K * 4) >> 4);   // +32 B per k-step inside the swizzle row
@@ -436,6 +505,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       tile_of(tile, iter, m_tile, chunk);
       const int64_t row = m_tile * TBM + q * 32 + lane;
       const int n0 = chunk * NC + half * H;
+      if constexpr (SLOT == 1) {
+        // ---- decimator (structured CQT): ONE K split per tile (K = 22 k-blocks = 132 accumulator updates: the truncation of the
+        //      tensor core's accumulation stays at the 4e-6 level the K splits of the long contraction are there to reach), so the
+        //      epilogue takes each row block straight from TMEM, 64 values at a time -- no running sums in registers.
+        //      tile row rho = (segment within the block) << bl | (row within the segment's group)
+        const SlotArgs& sl = prm.slots;
+        const int acc = (int)(it & 1u);
+        mbar_wait(bar_tfull(acc), (it >> 1) & 1u);
+        tc_fence_after();
+        ++it;
+        const int rho = q * 32 + lane;
+        const int sg = (int)(m_tile / sl.jgroups), jg = (int)(m_tile - (int64_t)sg * sl.jgroups);
+        const int bl = sl.box_log2, spb = 128 >> bl;                   // segments per row block
+        const int64_t slot = (int64_t)sg * MH * spb + (rho >> bl);     // of row block 0; block h: + spb * h
+        const int j = (jg << bl) + (rho & ((1 << bl) - 1));
+        const float scale = prm.out_scale * sl.plane_scale;            // both powers of two
+        // Row j holds outputs k = j * NC + n of the next octave; beyond the octave's length -> zeros (librosa fixes the length to
+        // ceil(n / 2), and the next stage must see a zero-extended signal).
+        // A thread owns 64 consecutive outputs of ONE row (128 bytes per plane), its neighbours rows 256 bytes further on: stored
+        // as they lie, every 16-byte vector is a memory request of its own -- 8 192 per tile through the SM's one request port,
+        // 4.2 us of a 17 us tile, and the TMA loads queue behind them (measured on B200: stage 1 of the inference recipe 330 us,
+        // 259 us without the stores).  So the 8 lanes of a group first transpose their 8 x 8 vectors (3 xor-butterfly rounds of
+        // shuffles): lane i then holds vector i of each of the group's 8 rows, and a store instruction writes 4 whole 128-byte
+        // lines.
+        static_assert(SLOT != 1 || H == 64, "decimator epilogue: 8 vectors of 8 halves per thread and plane");
+        const int i8 = lane & 7, g8 = lane & ~7;
+#pragma unroll
+        for (int h = 0; h < MH; ++h) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TMAXN + (uint32_t)(h * NC + half * H);
+          uint32_t v[64];
+#pragma unroll
+          for (int c = 0; c < 64; c += 16) tmem_ld16(taddr + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+          tmem_ld_wait();
+          if (h == MH - 1) {                                           // the accumulator stage is free for the tile after next
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty(acc));
+          }
+          const int64_t slot_h = slot + spb * h;
+          const int valid = slot_h < sl.n_slots ? halved_len(__ldg(sl.seg_len + slot_h), sl.stage_out) : 0;
+          const int k0 = j * NC + half * H;
+          uint4 chh[8], chl[8];                                        // hi and lo planes of the row's 64 values: 2 x 8 vectors
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t wh[4], wl[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = 8 * c + 2 * u;
+              const float v0 = (k0 + e < valid) ? __uint_as_float(v[e]) * scale : 0.f;
+              const float v1 = (k0 + e + 1 < valid) ? __uint_as_float(v[e + 1]) * scale : 0.f;
+              const __half2 hh = __floats2half2_rn(v0, v1);
+              const float2 hf = __half22float2(hh);
+              const __half2 ll = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+              wh[u] = *reinterpret_cast<const uint32_t*>(&hh);
+              wl[u] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            chh[c] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+            chl[c] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+          }
+          xpose8_round<4>(chh, i8); xpose8_round<2>(chh, i8); xpose8_round<1>(chh, i8);
+          xpose8_round<4>(chl, i8); xpose8_round<2>(chl, i8); xpose8_round<1>(chl, i8);
+          // ch?[r] = vector i8 of the row held by lane g8 + r
+          const int64_t col = sl.out_base + half * H + 8 * i8;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int rho_r = q * 32 + g8 + r;
+            const int64_t slot_r = (int64_t)sg * MH * spb + spb * h + (rho_r >> bl);
+            const int j_r = (jg << bl) + (rho_r & ((1 << bl) - 1));
+            if (slot_r < sl.n_slots) {
+              const int64_t at = col + slot_r * sl.out_stride + (int64_t)j_r * NC;
+              *reinterpret_cast<uint4*>(sl.out_hi + at) = chh[r];
+              *reinterpret_cast<uint4*>(sl.out_lo + at) = chl[r];
+            }
+          }
+        }
+        continue;
+      }
       const int n_sp = SCHED ? (s_sched_len[chunk] + prm.kb_per_split - 1) / prm.kb_per_split : n_splits;
       float sum[MH * H];
       for (int sp = 0; sp < n_sp; ++sp, ++it) {
@@ -511,30 +657,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         const int bl = sl.box_log2, spb = 128 >> bl;                   // segments per row block
         const int64_t slot = (int64_t)sg * MH * spb + (rho >> bl);     // of row block 0; block h: + spb * h
         const int j = (jg << bl) + (rho & ((1 << bl) - 1));
-        if (SLOT == 1) {
-          // decimator: row j holds outputs k = j * NC + n of the next octave; beyond the octave's length -> zeros (librosa
-          // fixes the length to ceil(n / 2), and the next stage must see a zero-extended signal)
-#pragma unroll
-          for (int h = 0; h < MH; ++h) {
-            const int64_t slot_h = slot + spb * h;
-            if (slot_h >= sl.n_slots) continue;
-            const int valid = halved_len(__ldg(sl.seg_len + slot_h), sl.stage_out);
-            __half* hi = sl.out_hi + sl.out_base + slot_h * sl.out_stride + (int64_t)j * NC + half * H;
-            __half* lo = sl.out_lo + sl.out_base + slot_h * sl.out_stride + (int64_t)j * NC + half * H;
-            const int k0 = j * NC + half * H;
-#pragma unroll
-            for (int c = 0; c < H; c += 8) {
-              __align__(16) __half h8[8], l8[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const float v = (k0 + c + u < valid) ? sum[h * H + c + u] * sl.plane_scale : 0.f;
-                h8[u] = __float2half_rn(v);
-                l8[u] = __float2half_rn(v - __half2float(h8[u]));
-              }
-              *reinterpret_cast<uint4*>(hi + c) = *reinterpret_cast<const uint4*>(h8);
-              *reinterpret_cast<uint4*>(lo + c) = *reinterpret_cast<const uint4*>(l8);
-            }
-          }
+        if constexpr (SLOT == 1) {
+          // (the decimator has its own epilogue above)
         } else {
           // response: row j = frame t of the segment, columns = (bin, {re, im}) of the octave's filters
           const int t = j;
@@ -803,6 +927,7 @@ int launch_gemm_tc(const PlanImpl& p, const void* d_xhi, const void* d_xlo, int6
   rc = encode_2d(&tm_xlo, d_xlo, (uint64_t)n_rows_alloc, (uint64_t)p.kp, TBM, p.elem_bytes);
   if (rc != GTC_OK) return rc;
   TcParams prm;
+  memset(&prm, 0, sizeof(prm));
   prm.nc = p.nc;
   prm.kb_per_split = (p.tc_kb_per_split > 0 ? p.tc_kb_per_split : 8) * (128 / TKB_BYTES);   // option counts 128-byte blocks
   prm.n_chunks = (int)ceil_div(p.n_out, prm.nc);
@@ -870,6 +995,8 @@ static int encode_3d(CUtensorMap* tm, const void* base, uint64_t k_extent, uint6
 int tc_slots_init() {
   GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128, false, true, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
   GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<32, false, true, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+  GTC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128, false, true, 0, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)RingRes<2>::smem_bytes));
   return GTC_OK;
 }
 
@@ -904,7 +1031,14 @@ int launch_gemm_tc_slots(const PlanImpl& p, const __half* x_hi, const __half* x_
   const unsigned grid = (unsigned)(prm.m_tiles < p.sm_count ? prm.m_tiles : p.sm_count);
   const CUtensorMap& tm_ohi = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_hi);
   const CUtensorMap& tm_olo = *reinterpret_cast<const CUtensorMap*>(p.tmap_op_lo);
-  if (slots.slot_mode == 1)
+  // decimator: resident master tile when the operator is Toeplitz with a whole-swizzle-group shift per k-block and fits it
+  const int nkb = p.kp / p.kb_elems;
+  prm.res_shift = p.res_shift;
+  const bool resident = slots.slot_mode == 1 && p.res_shift > 0 && p.res_shift % 8 == 0 && TBM % p.res_shift == 0 &&
+                        TBM + p.res_shift * (nkb - 1) <= kResRows && p.n_pad == TBM;
+  if (resident)
+    gemm_tc_kernel<128, false, true, 0, 1, false, true><<<grid, TC_THREADS, RingRes<2>::smem_bytes, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
+  else if (slots.slot_mode == 1)
     gemm_tc_kernel<128, false, true, 0, 1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
   else
     gemm_tc_kernel<32, false, true, 0, 2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);

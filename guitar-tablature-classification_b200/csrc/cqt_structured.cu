@@ -271,7 +271,10 @@ constexpr int kPlaneFront = 512;          // zero samples in front of segment 0 
 constexpr float kPlaneScale = 256.f;      // == the fp16x2 engine's x_scale (cqt_api.cu)
 
 struct TcGeom {
-  int64_t S[kMaxOctaves];                 // samples per segment slot of octave i (multiple of 256, >= len_i + guard)
+  int64_t S[kMaxOctaves];                 // samples per segment slot of octave i (multiple of 256, >= len_i + guard) = slot stride
+  int64_t R[kMaxOctaves];                 // samples of a slot the decimator computes: whole pairs of 128-output rows covering the
+                                          // LONGEST segment's octave-i length; [R, S) is zero-filled by pad_zero_kernel instead
+                                          // (the short low octaves of a 0.2 s window are 35-138 samples in 512-sample slots)
   int64_t plane_elems[kMaxOctaves];       // halves per plane
   size_t off_hi[kMaxOctaves], off_lo[kMaxOctaves];
   int t_pad;                              // frames per segment, padded to 8
@@ -284,12 +287,13 @@ static void tc_geometry(const SPlanImpl& p, int64_t n_seg, int64_t max_len, TcGe
   const int64_t guard = p.dec_left + 8 > p.n_fft / 2 ? p.dec_left + 8 : p.n_fft / 2;
   for (int i = 0; i < p.n_oct; ++i) {
     g.S[i] = round_up(len + guard, 256);                  // whole pairs of 128-output rows (the smallest TMA box is 64 segments x 2 rows)
+    g.R[i] = round_up(len, 256) < g.S[i] ? round_up(len, 256) : g.S[i];
     len = (len + 1) / 2;
   }
   for (int i = 0; i < p.n_oct; ++i) {
     // furthest sample any window of the last segment touches, past that segment's slot
     int64_t reach = (int64_t)g.t_pad * (p.hop >> i) + p.n_fft;                       // response frames
-    if (i + 1 < p.n_oct) reach = reach > 2 * g.S[i + 1] + p.dec_k ? reach : 2 * g.S[i + 1] + p.dec_k;   // decimator windows
+    if (i + 1 < p.n_oct) reach = reach > 2 * g.R[i + 1] + p.dec_k ? reach : 2 * g.R[i + 1] + p.dec_k;   // decimator windows
     const int64_t tail = reach > g.S[i] ? reach - g.S[i] : 0;
     g.plane_elems[i] = round_up(kPlaneFront + n_seg * g.S[i] + tail + 64, 512);
   }
@@ -301,6 +305,8 @@ static void tc_geometry(const SPlanImpl& p, int64_t n_seg, int64_t max_len, TcGe
 struct PadList {
   __half* plane[2 * kMaxOctaves];
   int64_t tail_at[2 * kMaxOctaves], tail_len[2 * kMaxOctaves];
+  int64_t slot_stride[2 * kMaxOctaves];   // per slot: samples [gap_at, slot_stride) are not written by any decimator row
+  int gap_at[2 * kMaxOctaves];
   int n;
   const int32_t* seg_len;       // also: frames kept per segment, for the response epilogues
   int32_t* seg_frames;
@@ -316,6 +322,14 @@ __global__ void __launch_bounds__(256) pad_zero_kernel(const PadList pl) {
     const int64_t total = kPlaneFront + pl.tail_len[i];
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x)
       p[k < kPlaneFront ? k : pl.tail_at[i] + (k - kPlaneFront)] = __float2half(0.f);
+    const int64_t gap = pl.slot_stride[i] - pl.gap_at[i];            // multiple of 256 samples: 16-byte vectors
+    if (gap > 0) {
+      const int64_t per = gap >> 3, vecs = pl.n_seg * per;
+      for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < vecs; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = k / per;
+        *reinterpret_cast<uint4*>(p + kPlaneFront + s * pl.slot_stride[i] + pl.gap_at[i] + ((k - s * per) << 3)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
   }
 }
 
@@ -402,9 +416,11 @@ static int run_structured_tc(const SPlanImpl& p, const In* d_audio, const int64_
         pl.plane[2 * i + h] = h ? lo(i) : hi(i);
         pl.tail_at[2 * i + h] = kPlaneFront + n_seg * g.S[i];
         pl.tail_len[2 * i + h] = g.plane_elems[i] - (kPlaneFront + n_seg * g.S[i]);
+        pl.slot_stride[2 * i + h] = g.S[i];
+        pl.gap_at[2 * i + h] = i == 0 ? (int)g.S[i] : (int)g.R[i];    // octave 0 is written whole by the split kernel
       }
     pl.seg_len = d_seg_len; pl.seg_frames = seg_frames; pl.n_seg = n_seg; pl.hop = p.hop; pl.n_oct = p.n_oct;
-    pad_zero_kernel<<<dim3(8, (unsigned)pl.n), 256, 0, st>>>(pl);
+    pad_zero_kernel<<<dim3(128, (unsigned)pl.n), 256, 0, st>>>(pl);
     GTC_CUDA_CHECK(cudaGetLastError());
   }
   {
@@ -426,7 +442,7 @@ static int run_structured_tc(const SPlanImpl& p, const In* d_audio, const int64_
     sl.out_hi = hi(i + 1); sl.out_lo = lo(i + 1);
     sl.out_stride = g.S[i + 1]; sl.out_base = kPlaneFront;
     sl.stage_out = i + 1;
-    int rc = launch_gemm_tc_slots(dec, hi(i), lo(i), kPlaneFront - p.dec_left, g.S[i], 256, (int)(g.S[i + 1] / 128), sl, st);
+    int rc = launch_gemm_tc_slots(dec, hi(i), lo(i), kPlaneFront - p.dec_left, g.S[i], 256, (int)(g.R[i + 1] / 128), sl, st);
     if (rc != GTC_OK) return rc;
   }
   sl.slot_mode = 2;
@@ -603,6 +619,18 @@ extern "C" int gtc_scqt_plan_create(gtc_splan** out, int device, int n_octaves, 
     int rc = tc_slots_init();
     if (rc == GTC_OK) rc = gtc_cqt_plan_create(&sub, device, p.dec_k, p.dec_k, 64, 1, op.data(), GTC_GEMM_TCGEN05_FP16X2);
     p.dec_plan = sub;
+    if (rc == GTC_OK && getenv("GTC_SCQT_STREAM_OP") == nullptr) {
+      // The operator is banded Toeplitz: k-block kb + 1 is k-block kb moved down by (elements per k-block) / 2 rows.  Verified on
+      // the values just built (the hi/lo split is elementwise, so the planes inherit it); the slotted GEMM then keeps ONE master
+      // tile of it resident in shared memory instead of streaming 16 KB of operator with every k-block (cqt_gemm_tc.cu: RES).
+      PlanImpl& dp = *reinterpret_cast<PlanImpl*>(sub);
+      const int e = dp.kb_elems, sh = e / 2;
+      bool toeplitz = p.dec_k % e == 0;
+      for (int n = sh; n < 128 && toeplitz; ++n)
+        for (int i = 0; i + e < p.dec_k; ++i)
+          if (op[(size_t)n * p.dec_k + i + e] != op[(size_t)(n - sh) * p.dec_k + i]) { toeplitz = false; break; }
+      dp.res_shift = toeplitz ? sh : 0;
+    }
     for (int i = 0; i < n_octaves && rc == GTC_OK; ++i) {
       std::vector<float> f((size_t)32 * n_fft, 0.f);
       for (int r = 0; r < n_real && r < 32; ++r)

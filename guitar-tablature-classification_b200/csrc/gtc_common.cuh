@@ -233,6 +233,10 @@ struct PlanImpl {
   void* d_op_maps;         // CUtensorMap[n_groups][2] in device memory: operator boxes of (g + 1) * grp_rows rows, hi / lo
   float sched_fill;        // scheduled tensor work / dense tensor work (1 = nothing to skip)
   int sched_rotate;        // 1: the N tile index is rotated by the CTA's iteration (balances tile types); 0: experiments
+  // ---- resident operator (slotted decimator GEMM): > 0 = the operator is banded Toeplitz, Op[n][i + kb_elems] == Op[n - res_shift][i],
+  //      so one master tile in shared memory serves every k-block (cqt_gemm_tc.cu, RingRes); set by cqt_structured.cu after it has
+  //      verified the property on the operator it built
+  int res_shift;
 };
 
 // launchers (each enqueues on `st`, returns a GTC_* code); xhi/xlo element type follows PlanImpl::elem_bytes
