@@ -20,6 +20,12 @@
 //                              partial sums added in fp32 RN registers, then re^2+im^2 + row max (or the raw complex
 //                              values) stored straight to global memory
 // The second audio row of a segment (hop = window/2, cqt.py:26-27) is just the TMA row coordinate + p.
+//
+// Slotted variants (SLOT = 1 decimator, 2 octave response) serve the structured CQT (cqt_structured.cu): rows are overlapping
+// windows of per-segment fp16 hi/lo planes (3-D tensor maps).  The decimator's banded Toeplitz operator is resident in shared
+// memory (RES, RingRes), its tile is one K split read straight from TMEM, and its epilogue transposes vectors across lanes so
+// that every store instruction writes whole 128-byte lines.  What was measured on the way (ring depth, L2 prefetch of the next
+// tile, TMA box shape, slot stride, no-MMA / no-load / no-store builds) is in profiles/r02t_decimator.md.
 #include <cuda.h>
 #include <stdlib.h>
 #include <type_traits>
@@ -99,6 +105,11 @@ struct TcParams {
   const CUtensorMap* op_maps;   // [n_groups][2] operator boxes of (g + 1) * grp_rows rows (hi, lo), device memory
   int sched_pitch, grp_rows, rotate;
   int res_shift;         // RES kernels: operator rows by which consecutive k-blocks of the Toeplitz operator are shifted
+  // SLOT == 1 (decimator): the band of the Toeplitz operator.  Entry e multiplies k-block band_kb[e] with the band_ng[e] groups of
+  // 16 operator rows starting at group band_g0[e] (tcgen05.mma with N = 16 * ng at accumulator column 16 * g0); entry 0 covers
+  // the whole tile (it zero-initialises the accumulator).  band_n == 0: every k-block against all rows.
+  int band_n;
+  uint8_t band_kb[kMaxBand], band_g0[kMaxBand], band_ng[kMaxBand];
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -384,9 +395,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         tile_of(tile, iter, m_tile, chunk);
         const int row0 = (int)(m_tile * TBM);
         const int n0 = chunk * NC;
-        const int n_ent = SCHED ? s_sched_len[chunk] : nkb;
+        const int n_ent = SCHED ? s_sched_len[chunk] : (SLOT == 1 && prm.band_n > 0) ? prm.band_n : nkb;
         for (int e = 0; e < n_ent; ++e) {
-          int kb = e, g0 = 0, rows = NC;
+          int kb = (SLOT == 1 && prm.band_n > 0) ? (int)prm.band_kb[e] : e, g0 = 0, rows = NC;
           if (SCHED) {
             const uint32_t w = s_sched[chunk * prm.sched_pitch + e];
             kb = (int)(w & 0xffffu); g0 = (int)((w >> 16) & 0xffu); rows = (int)(w >> 24) * prm.grp_rows;
@@ -438,7 +449,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
         int64_t m_tile; int chunk;
         tile_of(tile, iter, m_tile, chunk);
-        const int n_ent = SCHED ? s_sched_len[chunk] : nkb;
+        const int n_ent = SCHED ? s_sched_len[chunk] : (SLOT == 1 && prm.band_n > 0) ? prm.band_n : nkb;
         const int n_sp = SLOT == 1 ? 1 : SCHED ? (n_ent + prm.kb_per_split - 1) / prm.kb_per_split : n_splits;   // decimator: see its epilogue
         int kb = 0;                                          // entry index
         for (int sp = 0; sp < n_sp; ++sp, ++it) {
@@ -458,12 +469,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                 tmem_d += (uint32_t)(((w >> 16) & 0xffu) * prm.grp_rows);
               }
             }
+            int kbk = kb;                                   // the operator's k-block of this entry
+            uint32_t band_at = 0;                           // byte offset of the entry's first operator row inside the k-block tile
+            if (SLOT == 1 && prm.band_n > 0) {              // only the 16-row groups of the Toeplitz band that reach this k-block
+              kbk = (int)prm.band_kb[kb];
+              const uint32_t g0 = prm.band_g0[kb], ng = prm.band_ng[kb];
+              idesc_e = make_idesc(kHalf ? 0u : 2u, TBM, (int)(16u * ng));
+              tmem_d += 16u * g0;
+              band_at = 16u * g0 * TKB_BYTES;               // whole 8-row swizzle groups: the swizzle phase is unchanged
+            }
             mbar_wait(bar_full(stage), phase);
             tc_fence_after();
             const uint64_t dxh = make_swizzle_desc(st_xhi(stage)), dxl = make_swizzle_desc(st_xlo(stage));
-            const uint32_t res_at = RES ? (uint32_t)(prm.res_shift * (nkb - 1 - kb)) * TKB_BYTES : 0u;   // kb == the k-block (no schedule)
-            const uint64_t doh = make_swizzle_desc(RES ? res_hi + res_at : st_ohi(stage));
-            const uint64_t dol = make_swizzle_desc(RES ? res_lo + res_at : st_olo(stage));
+            const uint32_t res_at = RES ? (uint32_t)(prm.res_shift * (nkb - 1 - kbk)) * TKB_BYTES : 0u;
+            const uint64_t doh = make_swizzle_desc((RES ? res_hi + res_at : st_ohi(stage)) + band_at);
+            const uint64_t dol = make_swizzle_desc((RES ? res_lo + res_at : st_olo(stage)) + band_at);
 #ifdef TC_EXP_NO_MMA        // timing experiment only
             if (!RES)
 #endif
@@ -1034,6 +1054,13 @@ int launch_gemm_tc_slots(const PlanImpl& p, const __half* x_hi, const __half* x_
   // decimator: resident master tile when the operator is Toeplitz with a whole-swizzle-group shift per k-block and fits it
   const int nkb = p.kp / p.kb_elems;
   prm.res_shift = p.res_shift;
+  static const int band_env = getenv("GTC_SCQT_DENSE_BAND") ? atoi(getenv("GTC_SCQT_DENSE_BAND")) : 0;   // A/B: 1 = every k-block against all rows
+  if (slots.slot_mode == 1 && p.band_n > 0 && p.band_n <= kMaxBand && !band_env) {
+    prm.band_n = p.band_n;
+    memcpy(prm.band_kb, p.band_kb, (size_t)p.band_n);
+    memcpy(prm.band_g0, p.band_g0, (size_t)p.band_n);
+    memcpy(prm.band_ng, p.band_ng, (size_t)p.band_n);
+  }
   const bool resident = slots.slot_mode == 1 && p.res_shift > 0 && p.res_shift % 8 == 0 && TBM % p.res_shift == 0 &&
                         TBM + p.res_shift * (nkb - 1) <= kResRows && p.n_pad == TBM;
   if (resident)

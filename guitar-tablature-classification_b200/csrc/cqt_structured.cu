@@ -20,8 +20,11 @@
 // signals of every octave live as fp16 hi/lo planes (x * 2^8 split into two halves, 22 mantissa bits), one zero-guarded
 // slot per segment:
 //   split_kernel        audio (fp32 / int16 PCM) -> octave-0 planes
-//   decimator GEMM      rows = 128-output windows of 672 input samples (row step 256: overlapping TMA rows) x a fixed
-//                       banded Toeplitz operator [128][672] of the taps; epilogue writes the next octave's planes
+//   decimator GEMM      rows = 128-output windows of 704 input samples (row step 256: overlapping TMA rows) x a fixed
+//                       banded Toeplitz operator [128][704] of the taps, kept RESIDENT in shared memory as one master tile
+//                       (k-block kb + 1 of a Toeplitz operator is k-block kb moved down 16 rows); only the rows that cover
+//                       the longest segment's octave length are computed, the rest of a slot is zero-filled once per call;
+//                       epilogue transposes 8 x 8 vectors by shuffles and writes the next octave's planes as whole lines
 //   response GEMM       rows = frames (n_fft samples, row step hop_i) x the octave's filters [32][n_fft]; epilogue
 //                       writes |C|^2 into [seg][bin][t] and the segment maximum
 //   sfinish_kernel      in-place dB
@@ -277,12 +280,20 @@ struct TcGeom {
                                           // (the short low octaves of a 0.2 s window are 35-138 samples in 512-sample slots)
   int64_t plane_elems[kMaxOctaves];       // halves per plane
   size_t off_hi[kMaxOctaves], off_lo[kMaxOctaves];
-  int t_pad;                              // frames per segment, padded to 8
+  int t_pad;                              // frame rows per segment: t_max rounded up to a pair (the smallest TMA box is 64 segments x 2 rows)
 };
 
 static void tc_geometry(const SPlanImpl& p, int64_t n_seg, int64_t max_len, TcGeom& g) {
   const int t_max = frames_of((int)max_len, p.hop, p.n_oct);
-  g.t_pad = (int)round_up(t_max, 8);
+  // Frame rows per segment: a TMA box takes 8, 4 or 2 consecutive rows of a segment (16 / 32 / 64 segments per 128-row block).
+  // Fewer rows per segment and box mean shorter runs in the response epilogue's stores (a run = the box's frames of one bin) and
+  // more segment maxima per tile.  Measured on B200 (cqt.py recipe, 9 frames: 16 rows in 8-row boxes 147 us, 12 rows in 4-row
+  // boxes 149 us, 10 rows in 2-row boxes 135 us for the 8 response launches): a row costs ~1.3 x in a 4-row box and ~1.45 x in a
+  // 2-row box, so 9 frames take 10 rows and the 130 frames of a 3 s segment stay at 136.
+  {
+    const double c8 = (double)round_up(t_max, 8), c4 = 1.3 * (double)round_up(t_max, 4), c2 = 1.45 * (double)round_up(t_max, 2);
+    g.t_pad = (int)(c8 <= c4 && c8 <= c2 ? round_up(t_max, 8) : c4 <= c2 ? round_up(t_max, 4) : round_up(t_max, 2));
+  }
   int64_t len = max_len;
   const int64_t guard = p.dec_left + 8 > p.n_fft / 2 ? p.dec_left + 8 : p.n_fft / 2;
   for (int i = 0; i < p.n_oct; ++i) {
@@ -619,7 +630,7 @@ extern "C" int gtc_scqt_plan_create(gtc_splan** out, int device, int n_octaves, 
     int rc = tc_slots_init();
     if (rc == GTC_OK) rc = gtc_cqt_plan_create(&sub, device, p.dec_k, p.dec_k, 64, 1, op.data(), GTC_GEMM_TCGEN05_FP16X2);
     p.dec_plan = sub;
-    if (rc == GTC_OK && getenv("GTC_SCQT_STREAM_OP") == nullptr) {
+    if (rc == GTC_OK) {
       // The operator is banded Toeplitz: k-block kb + 1 is k-block kb moved down by (elements per k-block) / 2 rows.  Verified on
       // the values just built (the hi/lo split is elementwise, so the planes inherit it); the slotted GEMM then keeps ONE master
       // tile of it resident in shared memory instead of streaming 16 KB of operator with every k-block (cqt_gemm_tc.cu: RES).
@@ -629,7 +640,29 @@ extern "C" int gtc_scqt_plan_create(gtc_splan** out, int device, int n_octaves, 
       for (int n = sh; n < 128 && toeplitz; ++n)
         for (int i = 0; i + e < p.dec_k; ++i)
           if (op[(size_t)n * p.dec_k + i + e] != op[(size_t)(n - sh) * p.dec_k + i]) { toeplitz = false; break; }
-      dp.res_shift = toeplitz ? sh : 0;
+      dp.res_shift = (toeplitz && getenv("GTC_SCQT_STREAM_OP") == nullptr) ? sh : 0;    // the switch is for A/B runs and the bit-identity test
+      // The band: 389 taps against windows of 704 samples leave 45 % of the operator zero -- k-block kb only reaches the output rows
+      // n with 0 <= 2n + c + left - i < taps for some i of the block.  Per k-block the contiguous range of 16-row groups that hold
+      // a non-zero (tcgen05.mma N is a multiple of 16), a full k-block first because the first MMA initialises the accumulator.
+      const int nkb = p.dec_k / e;
+      std::vector<int> g0(nkb, -1), g1(nkb, -1);
+      for (int kb = 0; kb < nkb; ++kb)
+        for (int n = 0; n < 128; ++n)
+          for (int i = kb * e; i < (kb + 1) * e; ++i)
+            if (op[(size_t)n * p.dec_k + i] != 0.f) { if (g0[kb] < 0) g0[kb] = n / 16; g1[kb] = n / 16; break; }
+      int full = -1;
+      for (int kb = 0; kb < nkb && full < 0; ++kb)
+        if (g0[kb] == 0 && g1[kb] == 7) full = kb;
+      dp.band_n = 0;
+      if (full >= 0 && nkb <= kMaxBand) {
+        auto push = [&](int kb) {
+          dp.band_kb[dp.band_n] = (uint8_t)kb; dp.band_g0[dp.band_n] = (uint8_t)g0[kb]; dp.band_ng[dp.band_n] = (uint8_t)(g1[kb] - g0[kb] + 1);
+          ++dp.band_n;
+        };
+        push(full);
+        for (int kb = 0; kb < nkb; ++kb)
+          if (kb != full && g0[kb] >= 0) push(kb);
+      }
     }
     for (int i = 0; i < n_octaves && rc == GTC_OK; ++i) {
       std::vector<float> f((size_t)32 * n_fft, 0.f);

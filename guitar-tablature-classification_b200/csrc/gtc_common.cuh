@@ -197,6 +197,8 @@ struct SlotArgs {
   int n_bins, bin_lo, bin_cnt, t_max, hop0, n_oct;
 };
 
+constexpr int kMaxBand = 48;   // k-blocks of a decimator operator that can carry a band schedule (PlanImpl, TcParams)
+
 // ---- segment-operator plan (cqt_api.cu) -------------------------------------------------------------------
 struct PlanImpl {
   int device;
@@ -237,6 +239,10 @@ struct PlanImpl {
   //      so one master tile in shared memory serves every k-block (cqt_gemm_tc.cu, RingRes); set by cqt_structured.cu after it has
   //      verified the property on the operator it built
   int res_shift;
+  // ---- band schedule of the same operator: entry e = k-block band_kb[e] x the band_ng[e] groups of 16 operator rows from group
+  //      band_g0[e] on that hold a non-zero on it; entry 0 is a full k-block (zero-initialises the accumulator).  0 = dense.
+  int band_n;
+  uint8_t band_kb[kMaxBand], band_g0[kMaxBand], band_ng[kMaxBand];
 };
 
 // launchers (each enqueues on `st`, returns a GTC_* code); xhi/xlo element type follows PlanImpl::elem_bytes

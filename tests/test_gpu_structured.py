@@ -208,3 +208,37 @@ def test_tensor_core_path_equals_fp32_simt_path(lib, monkeypatch):
     d = p_tc.segments_db(pcm.to(torch.float32) / 32768.0, st, va, le, max(lens)).cpu().numpy()
     assert np.array_equal(c, d)
     p_tc.close(); p_simt.close()
+
+
+def test_resident_toeplitz_operator_equals_streamed_operator(lib, monkeypatch):
+    """The decimator GEMM keeps ONE master tile of its banded Toeplitz operator in shared memory and addresses k-block kb
+    as rows 16 (nkb-1-kb) .. +128 of it (cqt_gemm_tc.cu: RES); GTC_SCQT_STREAM_OP=1 at plan creation streams the operator's
+    own k-blocks through the TMA ring instead.  Same MMAs on the same operands in the same order: bit-identical features,
+    on ragged clips at both sample rates (different slot geometries: 16 x 8, 32 x 4 and 64 x 2 TMA boxes)."""
+    from gtc_b200 import ops, CqtRecipe
+    dev = torch.device("cuda")
+    for sr, lens in ((22050.0, [66150, 4410, 3000, 40000, 977] + [5000 + 613 * i for i in range(30)]),
+                     (44100.0, [44100, 30001, 256] + [12000 + 977 * i for i in range(15)])):
+        r = CqtRecipe(sr=sr)
+        clips = [make_test_audio(n, seed=300 + i, sr=sr) for i, n in enumerate(lens)]
+        off = np.concatenate([[0], np.cumsum(lens)])
+        st, va, le = seg_tables(off[:-1].tolist(), lens, lens, dev)
+        audio = torch.from_numpy(np.concatenate(clips)).to(dev)
+        p_res = ops.StructuredCqtPlan(r)
+        a = p_res.segments_db(audio, st, va, le, max(lens)).cpu().numpy()
+        monkeypatch.setenv("GTC_SCQT_STREAM_OP", "1")
+        p_str = ops.StructuredCqtPlan(r)
+        monkeypatch.delenv("GTC_SCQT_STREAM_OP")
+        b = p_str.segments_db(audio, st, va, le, max(lens)).cpu().numpy()
+        assert np.isfinite(a).all() and np.array_equal(a, b), f"sr {sr}"
+        # the workspace is reused: a second call with SHORTER segments must not see the first call's samples in the slot gaps
+        short = [max(64, n // 3) for n in lens]
+        st2, va2, le2 = seg_tables(off[:-1].tolist(), short, short, dev)
+        c = p_res.segments_db(audio, st2, va2, le2, max(lens)).cpu().numpy()
+        d = p_str.segments_db(audio, st2, va2, le2, max(short)).cpu().numpy()
+        for i, n in enumerate(short):
+            T = p_res.frames(n)
+            x, y = c[i, :, :T], d[i, :, :T]
+            both = (x > -59.9) & (y > -59.9)
+            assert both.sum() > 0 and np.abs(x - y)[both].max() < 1e-3, f"sr {sr} clip {i}: slot gaps"
+        p_res.close(); p_str.close()
