@@ -403,8 +403,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             kb = (int)(w & 0xffffu); g0 = (int)((w >> 16) & 0xffu); rows = (int)(w >> 24) * prm.grp_rows;
           }
           mbar_wait(bar_empty(stage), phase ^ 1);
-#ifdef TC_EXP_NO_XLOAD      // timing experiment only: no operand traffic at all in the resident kernels
-          if (RES) { mbar_arrive(bar_full(stage)); if (++stage == NSTAGES) { stage = 0; phase ^= 1; } continue; }
+#ifdef TC_EXP_NO_XLOAD      // timing experiment only: no operand traffic at all in the slotted kernels
+          if (SLOT > 0) { mbar_arrive(bar_full(stage)); if (++stage == NSTAGES) { stage = 0; phase ^= 1; } continue; }
 #endif
           mbar_expect_tx(bar_full(stage), rows == NC ? stage_tx : 2 * X_TILE_BYTES + 2 * (uint32_t)rows * TBK * 4);
           const int p = kb / prm.kb_per_part;
@@ -485,7 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             const uint64_t doh = make_swizzle_desc((RES ? res_hi + res_at : st_ohi(stage)) + band_at);
             const uint64_t dol = make_swizzle_desc((RES ? res_lo + res_at : st_olo(stage)) + band_at);
 #ifdef TC_EXP_NO_MMA        // timing experiment only
-            if (!RES)
+            if (SLOT == 0)
 #endif
 #pragma unroll
             for (int k = 0; k < TBK / TUMMA_K; ++k) {
@@ -692,6 +692,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             for (int c = 0; c < H; c += 2) {
               const int b = (half * H + c) >> 1;
               const float m = valid ? sum[h * H + c] * sum[h * H + c] + sum[h * H + c + 1] * sum[h * H + c + 1] : 0.f;
+#ifdef TC_EXP_NO_STORE2     // timing experiment only: the response epilogue without its stores
+              if (m == 12345.f)
+#endif
               if (live_h && t < sl.t_max && b < sl.bin_cnt) {
                 sl.out[(slot_h * sl.n_bins + sl.bin_lo + b) * sl.t_max + t] = m;
                 mx = fmaxf(mx, m);
