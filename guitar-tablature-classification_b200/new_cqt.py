@@ -55,6 +55,18 @@ def _save_picture(path_noext, db):
         pass
 
 
+def picture_stems(audio_name, file_num, offsets):
+    """Output names of one file's windows, new_cqt.py:40: ``{audio_name}_segment_{file_num}_{start:.2f}`` -- the names
+    jam_to_tablature.py later gives its label files (tests/test_reference_golden.py checks them against the 43 188 label
+    files the reference repository ships)."""
+    return [f"{audio_name}_segment_{file_num}_{off:.2f}" for off in offsets]
+
+
+def window_offsets(start, dur, max_images, total_files):
+    """Window starts of every file, new_cqt.py:53-61: ``max_images // total_files`` windows, ``dur`` apart."""
+    return [start + j * dur for j in range(max_images // total_files)]
+
+
 def _process_file(file_num, offsets, dur):
     files = _audio_files()
     name = files[file_num]
@@ -67,8 +79,8 @@ def _process_file(file_num, offsets, dur):
     recipe = CqtRecipe(sr=CQT_SR, window_size=dur, hop_size=dur)
     feats = features.clips_features(segs, recipe, seg_len=w, seg_hop=w)       # every window is its own one-segment clip
     os.makedirs(OUTPUT_DIR, exist_ok=True)
-    for off, f in zip(kept, feats):
-        out = os.path.join(OUTPUT_DIR, f"{audio_name}_segment_{file_num}_{off:.2f}")
+    for stem, f in zip(picture_stems(audio_name, file_num, kept), feats):
+        out = os.path.join(OUTPUT_DIR, stem)
         _save_picture(out, f[0])
         print(f"Saved: {out}.png")
     return len(kept)
@@ -83,10 +95,10 @@ def process_all_files_parallel(start, dur=0.2, max_images=45000):
     if total_files == 0:
         print(f"No .wav files in {AUDIO_DIR}")
         return 0
-    num_images_per_file = max_images // total_files
+    offsets = window_offsets(start, dur, max_images, total_files)
     done = 0
     for i in range(total_files):
-        done += _process_file(i, [start + j * dur for j in range(num_images_per_file)], dur)
+        done += _process_file(i, offsets, dur)
     return done
 
 

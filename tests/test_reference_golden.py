@@ -241,3 +241,25 @@ def test_gpu_cqt_driver_matches_reference(lib, tmp_path):
         assert near.mean() < 0.01
         assert np.all(np.abs(np.where(a == -120.0, want, a)[near] + 60.0) < 0.02)
     assert worst < 0.01, worst
+
+
+def test_window_picture_names_match_the_label_files_the_reference_ships():
+    """The reference repository ships the 43 188 label files of its own GuitarSet run (tablatures/), each named after the
+    window picture new_cqt.py:40 wrote for it: 360 clips x (45000 // 360 = 125) windows, fewer where a clip ends earlier.
+    The drop-in's naming and window-offset helpers regenerate that listing exactly (sha256 of the sorted names; compared
+    name by name as well where /root/reference is mounted)."""
+    import hashlib
+    import new_cqt
+    fx = json.load(open(os.path.join(GOLD, "ref_tablature_listing.json")))
+    clips, windows = fx["clips"], fx["windows"]
+    assert len(clips) == 360 and max(windows) == 45000 // 360
+    offsets = new_cqt.window_offsets(0, 0.2, 45000, len(clips))
+    names = []
+    for file_num, (clip, n) in enumerate(zip(clips, windows)):      # windows past the end of a file are skipped: the first n stay
+        names += [s + ".npy" for s in new_cqt.picture_stems(clip, file_num, offsets[:n])]
+    names.sort()
+    assert len(names) == fx["n_files"]
+    assert hashlib.sha256("\n".join(names).encode()).hexdigest() == fx["sha256_sorted_listing"]
+    ref_dir = "/root/reference/tablatures"
+    if os.path.isdir(ref_dir):
+        assert names == sorted(os.listdir(ref_dir))
