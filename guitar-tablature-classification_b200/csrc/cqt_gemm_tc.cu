@@ -677,9 +677,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         const int bl = sl.box_log2, spb = 128 >> bl;                   // segments per row block
         const int64_t slot = (int64_t)sg * MH * spb + (rho >> bl);     // of row block 0; block h: + spb * h
         const int j = (jg << bl) + (rho & ((1 << bl) - 1));
-        if constexpr (SLOT == 1) {
-          // (the decimator has its own epilogue above)
-        } else {
+        if constexpr (SLOT == 2) {                                     // (the decimator, SLOT == 1, has its own epilogue above)
           // response: row j = frame t of the segment, columns = (bin, {re, im}) of the octave's filters
           const int t = j;
 #pragma unroll
