@@ -345,10 +345,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     for (int i = threadIdx.x; i < prm.n_chunks * prm.sched_pitch; i += blockDim.x) s_sched[i] = __ldg(prm.sched + i);
     if (threadIdx.x < prm.n_chunks) s_sched_len[threadIdx.x] = __ldg(prm.sched_len + threadIdx.x);
   }
+  if (SLOT > 0) pdl_launch_dependents();          // structured CQT chain: the next kernel may start its prologue
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_slot;
+  if (SLOT > 0) pdl_wait();                       // ... and this one touches its operands only after its predecessor has completed
 
   const int nkb = prm.parts * prm.kb_per_part;
   const int n_splits = (nkb + prm.kb_per_split - 1) / prm.kb_per_split;
@@ -1064,12 +1066,14 @@ int launch_gemm_tc_slots(const PlanImpl& p, const __half* x_hi, const __half* x_
   }
   const bool resident = slots.slot_mode == 1 && p.res_shift > 0 && p.res_shift % 8 == 0 && TBM % p.res_shift == 0 &&
                         TBM + p.res_shift * (nkb - 1) <= kResRows && p.n_pad == TBM;
+  static const bool pdl = getenv("GTC_SCQT_NO_PDL") == nullptr;                             // programmatic dependent launch (gtc_common.cuh)
   if (resident)
-    gemm_tc_kernel<128, false, true, 0, 1, false, true><<<grid, TC_THREADS, RingRes<2>::smem_bytes, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
+    GTC_CUDA_CHECK(launch_pdl(gemm_tc_kernel<128, false, true, 0, 1, false, true>, dim3(grid), dim3(TC_THREADS), RingRes<2>::smem_bytes, st, pdl,
+                              tm_xhi, tm_xlo, tm_ohi, tm_olo, prm));
   else if (slots.slot_mode == 1)
-    gemm_tc_kernel<128, false, true, 0, 1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
+    GTC_CUDA_CHECK(launch_pdl(gemm_tc_kernel<128, false, true, 0, 1>, dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, st, pdl, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm));
   else
-    gemm_tc_kernel<32, false, true, 0, 2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, prm);
+    GTC_CUDA_CHECK(launch_pdl(gemm_tc_kernel<32, false, true, 0, 2>, dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, st, pdl, tm_xhi, tm_xlo, tm_ohi, tm_olo, prm));
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;
 }

@@ -250,6 +250,8 @@ response_kernel(const In* __restrict__ src, const int64_t* __restrict__ seg_star
 __global__ void __launch_bounds__(256)
 sfinish_kernel(float* __restrict__ io, const float* __restrict__ segmax, int64_t n_seg, int per_seg, float power,
                float amin, float top_db, float cut_db, float floor_db) {
+  pdl_launch_dependents();
+  pdl_wait();                              // tensor path: launched behind the last response GEMM (gtc_common.cuh)
   const int64_t total = n_seg * per_seg;
   if ((per_seg & 3) == 0) {
     float4* io4 = reinterpret_cast<float4*>(io);
@@ -325,6 +327,7 @@ struct PadList {
   int hop, n_oct;
 };
 __global__ void __launch_bounds__(256) pad_zero_kernel(const PadList pl) {
+  pdl_launch_dependents();                 // launched normally (its predecessor is a memset); the split kernel may overlap its tail
   if (blockIdx.y == 0)
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < pl.n_seg; s += (int64_t)gridDim.x * blockDim.x)
       pl.seg_frames[s] = frames_of(__ldg(pl.seg_len + s), pl.hop, pl.n_oct);
@@ -349,6 +352,8 @@ template <typename In>
 __global__ void __launch_bounds__(256)
 split_kernel(const In* __restrict__ audio, const int64_t* __restrict__ seg_start, const int32_t* __restrict__ seg_valid,
              const int32_t* __restrict__ seg_len, int64_t n_seg, int64_t S, __half* __restrict__ hi, __half* __restrict__ lo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t per_seg = S >> 3;
   const int64_t total = n_seg * per_seg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -438,7 +443,9 @@ static int run_structured_tc(const SPlanImpl& p, const In* d_audio, const int64_
     int64_t blocks = ceil_div(n_seg * (g.S[0] >> 3), 256);
     const int64_t cap = (int64_t)p.sm_count * 32;
     if (blocks > cap) blocks = cap;
-    split_kernel<In><<<(unsigned)blocks, 256, 0, st>>>(d_audio, d_seg_start, d_seg_valid, d_seg_len, n_seg, g.S[0], hi(0), lo(0));
+    static const bool pdl = getenv("GTC_SCQT_NO_PDL") == nullptr;
+    GTC_CUDA_CHECK(launch_pdl(split_kernel<In>, dim3((unsigned)blocks), dim3(256), 0, st, pdl, d_audio, d_seg_start, d_seg_valid, d_seg_len, n_seg,
+                              g.S[0], hi(0), lo(0)));
     GTC_CUDA_CHECK(cudaGetLastError());
   }
   SlotArgs sl;
@@ -470,7 +477,9 @@ static int run_structured_tc(const SPlanImpl& p, const In* d_audio, const int64_
   const int64_t cap = (int64_t)p.sm_count * 16;
   if (fblocks > cap) fblocks = cap;
   if (fblocks < 1) fblocks = 1;
-  sfinish_kernel<<<(unsigned)fblocks, 256, 0, st>>>(d_out, segmax, n_seg, per_seg, power, amin, top_db, cut_db, floor_db);
+  static const bool pdl = getenv("GTC_SCQT_NO_PDL") == nullptr;
+  GTC_CUDA_CHECK(launch_pdl(sfinish_kernel, dim3((unsigned)fblocks), dim3(256), 0, st, pdl, d_out, (const float*)segmax, n_seg, per_seg, power, amin,
+                            top_db, cut_db, floor_db));
   GTC_CUDA_CHECK(cudaGetLastError());
   return GTC_OK;
 }

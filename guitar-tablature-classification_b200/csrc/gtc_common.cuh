@@ -47,6 +47,27 @@ int sm_count_of_current_device();
 int patch_max_ctas();
 int patch_ctas_per_sm();
 
+// ---- programmatic dependent launch (structured CQT chain: 17-19 short kernels back to back).  A kernel launched with the
+// attribute may start while its predecessor in the stream is still draining: it runs its prologue (barrier init, TMEM
+// allocation, the resident operator tile) and then waits in pdl_wait() until the predecessor grid has completed and its
+// writes are visible.  EVERY kernel of such a chain calls pdl_wait() before its first dependent access (completion is then
+// transitive); in a kernel launched normally both calls are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // index of the clip owning global item `g`:  largest c with off[c] <= g   (off has n+1 monotone entries)
 __device__ __forceinline__ int find_clip(const int64_t* __restrict__ off, int n, int64_t g) {
   int lo = 0, hi = n;              // invariant: off[lo] <= g < off[hi]
