@@ -455,22 +455,35 @@ static int run_structured_tc(const SPlanImpl& p, const In* d_audio, const int64_
   sl.seg_frames = seg_frames;
   sl.plane_scale = kPlaneScale;
   const PlanImpl& dec = *reinterpret_cast<const PlanImpl*>(p.dec_plan);
-  for (int i = 0; i + 1 < p.n_oct; ++i) {                 // octave i+1 = 2:1 decimation of octave i
-    sl.slot_mode = 1;
-    sl.out_hi = hi(i + 1); sl.out_lo = lo(i + 1);
-    sl.out_stride = g.S[i + 1]; sl.out_base = kPlaneFront;
-    sl.stage_out = i + 1;
-    int rc = launch_gemm_tc_slots(dec, hi(i), lo(i), kPlaneFront - p.dec_left, g.S[i], 256, (int)(g.R[i + 1] / 128), sl, st);
-    if (rc != GTC_OK) return rc;
-  }
-  sl.slot_mode = 2;
-  sl.out = d_out; sl.segmax = segmax;
-  sl.n_bins = p.n_bins; sl.t_max = t_max; sl.hop0 = p.hop; sl.n_oct = p.n_oct;
-  for (int i = 0; i < p.n_oct; ++i) {
-    sl.bin_lo = p.bin_lo[i]; sl.bin_cnt = p.bin_cnt[i];
+  // Launch order: the response of octave i right after the decimation that produced it (and before the one that consumes it), so
+  // that the planes of the small octaves are still in L2 for both readers.  GTC_SCQT_ORDER=1: all decimations, then all responses.
+  static const bool grouped = getenv("GTC_SCQT_ORDER") != nullptr && atoi(getenv("GTC_SCQT_ORDER")) == 1;
+  auto decimate = [&](int i) {                            // octave i+1 = 2:1 decimation of octave i
+    SlotArgs d = sl;
+    d.slot_mode = 1;
+    d.out_hi = hi(i + 1); d.out_lo = lo(i + 1);
+    d.out_stride = g.S[i + 1]; d.out_base = kPlaneFront;
+    d.stage_out = i + 1;
+    return launch_gemm_tc_slots(dec, hi(i), lo(i), kPlaneFront - p.dec_left, g.S[i], 256, (int)(g.R[i + 1] / 128), d, st);
+  };
+  auto respond = [&](int i) {
+    SlotArgs r = sl;
+    r.slot_mode = 2;
+    r.out = d_out; r.segmax = segmax;
+    r.n_bins = p.n_bins; r.t_max = t_max; r.hop0 = p.hop; r.n_oct = p.n_oct;
+    r.bin_lo = p.bin_lo[i]; r.bin_cnt = p.bin_cnt[i];
     const PlanImpl& rp = *reinterpret_cast<const PlanImpl*>(p.resp_plan[i]);
-    int rc = launch_gemm_tc_slots(rp, hi(i), lo(i), kPlaneFront - p.n_fft / 2, g.S[i], p.hop >> i, g.t_pad, sl, st);
-    if (rc != GTC_OK) return rc;
+    return launch_gemm_tc_slots(rp, hi(i), lo(i), kPlaneFront - p.n_fft / 2, g.S[i], p.hop >> i, g.t_pad, r, st);
+  };
+  if (grouped) {
+    for (int i = 0; i + 1 < p.n_oct; ++i) { int rc = decimate(i); if (rc != GTC_OK) return rc; }
+    for (int i = 0; i < p.n_oct; ++i) { int rc = respond(i); if (rc != GTC_OK) return rc; }
+  } else {
+    for (int i = 0; i < p.n_oct; ++i) {
+      int rc = respond(i);
+      if (rc == GTC_OK && i + 1 < p.n_oct) rc = decimate(i);
+      if (rc != GTC_OK) return rc;
+    }
   }
   const int per_seg = p.n_bins * t_max;
   int64_t fblocks = ceil_div(n_seg * per_seg, 256 * 4);
