@@ -104,3 +104,54 @@ def test_operator_zero_structure_at_mma_granularity():
     assert abs(np.mean(fill) - 0.694) < 0.01             # 31 % of the tensor work multiplied zeros
     # whole-k-block skipping alone would reach far less: the union over a tile's five frames covers most of the segment
     assert kblocks(nz[:, 72:96].any(axis=(0, 1, 2))).mean() > 0.69
+
+
+def test_toeplitz_decimator_operator_structure():
+    """The structure the resident-operator decimator GEMM relies on (csrc/cqt_structured.cu builds the operator, csrc/cqt_gemm_tc.cu
+    `RES` / `band_*` use it), restated on the product's tap table:
+      * Op[n][i] = h[2n + c + left - i] is Toeplitz: k-block kb + 1 (32 samples) is k-block kb moved down 16 rows;
+      * one master tile of 128 + 16 (nkb - 1) rows, filled by 128-row boxes of k-blocks nkb-1, nkb-9, ... and, once those run out,
+        of k-block 0 from row r - 16 (nkb - 1) on, holds every k-block kb at rows 16 (nkb - 1 - kb) .. + 128;
+      * per k-block the non-zero rows are one contiguous range of 16-row groups, a full k-block exists (it initialises the
+        accumulator), and the band is 120 of the 176 group-blocks (the tensor work the schedule keeps);
+      * the GEMM of overlapping windows against it is the decimator: y[k] = sum_m h[m] x[2k + c - m]."""
+    h = cd.decimator_taps().astype(np.float32)
+    taps, c = len(h), (len(h) - 1) // 2
+    E, sh, rows = 32, 16, 128
+    left = -(-c // 32) * 32
+    K = -(-(left + 254 + c + 1) // 32) * 32
+    assert (taps, c, left, K) == (389, 194, 224, 704)
+    n, i = np.arange(rows)[:, None], np.arange(K)[None, :]
+    m = 2 * n + c + left - i
+    op = np.where((m >= 0) & (m < taps), h[np.clip(m, 0, taps - 1)], 0.0).astype(np.float32)
+    nkb = K // E
+    assert np.array_equal(op[sh:, E:], op[:-sh, :-E])                                   # the shift property
+    master = np.full((rows + sh * (nkb - 1) + rows, E), np.nan, np.float32)               # box-sized slack at the end
+    need = rows + sh * (nkb - 1)
+    for r in range(0, need, rows):
+        kb = nkb - 1 - r // sh
+        if kb >= 0:
+            master[r:r + rows] = op[:, kb * E:(kb + 1) * E]
+        else:
+            n0 = r - sh * (nkb - 1)
+            master[r:r + rows - n0] = op[n0:, :E]
+            master[r + rows - n0:r + rows] = 0.0                                           # TMA zero-fills rows past the operator
+    assert not np.isnan(master[:need]).any()
+    for kb in range(nkb):
+        at = sh * (nkb - 1 - kb)
+        assert np.array_equal(master[at:at + rows], op[:, kb * E:(kb + 1) * E]), kb
+    work, full = 0, 0
+    for kb in range(nkb):
+        nz = np.flatnonzero(np.any(op[:, kb * E:(kb + 1) * E] != 0, axis=1))
+        groups = np.unique(nz // 16)
+        assert len(groups) and np.array_equal(groups, np.arange(groups[0], groups[-1] + 1))   # contiguous
+        work += len(groups)
+        full += len(groups) == rows // 16
+    assert full >= 1 and work == 120 and nkb * (rows // 16) == 176
+    # windows x operator == the 2:1 decimator (zero-extended signal, group delay c)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(3000)
+    xz = np.concatenate([np.zeros(left), x, np.zeros(K)])
+    y = np.array([op.astype(np.float64) @ xz[256 * j: 256 * j + K] for j in range(4)]).reshape(-1)
+    ref = np.array([sum(h[mm] * (x[2 * k + c - mm] if 0 <= 2 * k + c - mm < len(x) else 0.0) for mm in range(taps)) for k in range(0, 512, 37)])
+    assert np.abs(y[0:512:37] - ref).max() < 1e-5 * np.abs(ref).max()
