@@ -1,5 +1,8 @@
+"""The structured inference recipe (tablature_generator.py:599-666) on 1 / 4 / 16 / 64 songs of 60 s, one call each: what a single
+song costs, and what programmatic dependent launch (GTC_SCQT_NO_PDL=1 turns it off) is worth at each size."""
 import os, sys, json
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/guitar-tablature-classification_b200")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "guitar-tablature-classification_b200"))
 import numpy as np, torch
 from gtc_b200 import synth
 from gtc_b200.inference import TabCnnFrontEnd
