@@ -105,6 +105,7 @@ struct TcParams {
   const CUtensorMap* op_maps;   // [n_groups][2] operator boxes of (g + 1) * grp_rows rows (hi, lo), device memory
   int sched_pitch, grp_rows, rotate;
   int res_shift;         // RES kernels: operator rows by which consecutive k-blocks of the Toeplitz operator are shifted
+  int reverse;           // slotted kernels: walk the tiles from the last segment to the first
   // SLOT == 1 (decimator): the band of the Toeplitz operator.  Entry e multiplies k-block band_kb[e] with the band_ng[e] groups of
   // 16 operator rows starting at group band_g0[e] (tcgen05.mma with N = 16 * ng at accumulator column 16 * g0); entry 0 covers
   // the whole tile (it zero-initialises the accumulator).  band_n == 0: every k-block against all rows.
@@ -361,6 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   // (Passes over the N tiles in order of cost balance better on paper and measured 14 % SLOWER: each pass re-reads all X
   // rows from HBM -- 4.7 TB/s in the dense passes.)
   auto tile_of = [&](int64_t tile, int iter, int64_t& m_tile, int& chunk) {
+    if (SLOT > 0 && prm.reverse) tile = n_tiles - 1 - tile;      // last segments first: the ones the previous kernel wrote last
     m_tile = tile / prm.n_chunks;
     chunk = (int)(tile - m_tile * prm.n_chunks);
     if (SCHED && prm.rotate) chunk = (chunk + iter) % prm.n_chunks;
@@ -1057,6 +1059,11 @@ int launch_gemm_tc_slots(const PlanImpl& p, const __half* x_hi, const __half* x_
   // decimator: resident master tile when the operator is Toeplitz with a whole-swizzle-group shift per k-block and fits it
   const int nkb = p.kp / p.kb_elems;
   prm.res_shift = p.res_shift;
+  // The producer of a plane (split kernel, decimator) writes it from the first segment to the last, and only the last ~100 MB are
+  // still in L2 when it ends.  The response reads its plane backwards (hot end first) and so leaves the HEAD hot for the decimator
+  // that reads the same plane next, forwards (cqt_structured.cu launches them in that order).  GTC_SCQT_FORWARD=1: both forwards.
+  static const bool fwd_env = getenv("GTC_SCQT_FORWARD") != nullptr;
+  prm.reverse = slots.slot_mode == 2 && !fwd_env;
   static const int band_env = getenv("GTC_SCQT_DENSE_BAND") ? atoi(getenv("GTC_SCQT_DENSE_BAND")) : 0;   // A/B: 1 = every k-block against all rows
   if (slots.slot_mode == 1 && p.band_n > 0 && p.band_n <= kMaxBand && !band_env) {
     prm.band_n = p.band_n;
